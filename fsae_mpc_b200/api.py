@@ -1,0 +1,233 @@
+"""Host-side mirror of the reference's LTV-MPC call surface, batched, on one B200.
+
+The reference host language is MATLAB (not available in this image); this module is the
+Python twin of the MEX shim described in INTEGRATION.md and keeps the reference's
+function names, argument meaning and outputs:
+
+    reference (MATLAB, one problem)                       here (B problems)
+    ---------------------------------------------------------------------------------
+    kappa = @(s) interpolate_curvature(s, xs, ys, dl)     mpc.set_track(id, xs, ys, dl)
+    rk2_kinematic_curvilinear(x, u, kappa, dt)            mpc.linearise(KINEMATIC, x, u, dt)
+    sequential_integration + *_state_constraints
+        + generate_qp                                     mpc.condense(KINEMATIC, ...)
+    ltvmpc_kinetmatic_curvilinear(x0,x_ref,kappa,dt,
+                                  x_lin,u_lin,QP)         mpc.ltvmpc_kinetmatic_curvilinear(...)
+    ltvmpc_dynamic_curvilinear(...)                       mpc.ltvmpc_dynamic_curvilinear(...)
+
+Array layout: every per-problem matrix is passed in the C-ABI's memory layout, which is
+MATLAB's column-major with the batch trailing.  As C-contiguous numpy arrays that reads
+    x0 (B, N_x)   x_ref, x_lin (B, N_steps, N_x)   u_lin (B, N_steps, N_u)
+    u_opt (B, N_steps*N_u)   x_opt (B, N_steps*N_x)    [== the reference's stacked vectors]
+
+No CPU fallback: constructing FsaeMpc without the built CUDA library or without an
+sm_100 GPU raises.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import Params, MODEL_KINEMATIC, MODEL_DYNAMIC
+
+KINEMATIC = MODEL_KINEMATIC
+DYNAMIC = MODEL_DYNAMIC
+_DIMS = {KINEMATIC: (5, 2, 1), DYNAMIC: (7, 2, 4)}
+
+
+class FsaeError(RuntimeError):
+    pass
+
+
+@dataclass
+class MpcResult:
+    """Outputs of ltvmpc_*_curvilinear.m:1 for B problems (+ solver diagnostics)."""
+    u_opt: np.ndarray        # (B, N_u*N)
+    x_opt: np.ndarray        # (B, N_x*N)
+    exitflag: np.ndarray     # (B,) int32, qpOASES convention
+    fval: np.ndarray         # (B,)
+    slack_opt: np.ndarray    # (B, N_soft)
+    iters: np.ndarray        # (B,) int32 active-set iterations
+    workingSetB: np.ndarray  # (B, nV) int8
+    workingSetC: np.ndarray  # (B, nC) int8
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _f64(a, shape):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.shape != shape:
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+def default_params(model=KINEMATIC):
+    p = Params()
+    _lib.load().fsae_default_params(model, C.byref(p))
+    return p
+
+
+class FsaeMpc:
+    """One context = one GPU + one stream + its track / parameter tables."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        rc = self._lib.fsae_create(C.byref(self._ctx), int(device))
+        if rc != 0:
+            self._ctx = None
+            raise FsaeError(
+                f"fsae_create(device={device}) failed with {rc}: an sm_100 (B200) GPU is required; "
+                "there is no CPU fallback")
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.fsae_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.fsae_last_error(self._ctx)
+            raise FsaeError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # ------------------------------------------------------------------ tables
+    def set_track(self, track_id, x_spline, y_spline, dl):
+        """main.m:15-18: the arclength spline behind `kappa`.  x_spline/y_spline (n_seg, 4)."""
+        xs = np.asfortranarray(x_spline, dtype=np.float64)
+        ys = np.asfortranarray(y_spline, dtype=np.float64)
+        if xs.ndim != 2 or xs.shape[1] != 4 or ys.shape != xs.shape:
+            raise ValueError("spline coefficient matrices must be (n_seg, 4)")
+        self._check(self._lib.fsae_set_track(self._ctx, int(track_id), _dp(xs), _dp(ys),
+                                             xs.shape[0], float(dl)), "fsae_set_track")
+
+    def set_params(self, param_id, params):
+        self._check(self._lib.fsae_set_params(self._ctx, int(param_id), C.byref(params)), "fsae_set_params")
+
+    # ------------------------------------------------------------------ stages
+    def interpolate_curvature(self, s, track_id=0):
+        """spline/interpolate_curvature.m:1."""
+        s = np.ascontiguousarray(s, dtype=np.float64).reshape(-1)
+        out = np.empty_like(s)
+        self._check(self._lib.fsae_interpolate_curvature_host(self._ctx, int(track_id), _dp(s), s.size, _dp(out)),
+                    "fsae_interpolate_curvature_host")
+        return out
+
+    def _ids(self, B, track_id, param_id):
+        t = None if track_id is None else np.ascontiguousarray(track_id, dtype=np.int32).reshape(B)
+        p = None if param_id is None else np.ascontiguousarray(param_id, dtype=np.int32).reshape(B)
+        return t, p
+
+    def linearise(self, model, x_lin, u_lin, dt, track_id=None, param_id=None):
+        """{euler,rk2,rk4}_{kinematic,dynamic}_curvilinear.m (scheme = params.lin_scheme).
+        Returns A (B,N,NX,NX), Bm (B,N,NX,NU), d (B,N,NX) with A[b,k] the k-th matrix."""
+        NX, NU, _ = _DIMS[model]
+        x_lin = np.ascontiguousarray(x_lin, dtype=np.float64)
+        B, N = x_lin.shape[0], x_lin.shape[1]
+        x_lin = _f64(x_lin, (B, N, NX))
+        u_lin = _f64(u_lin, (B, N, NU))
+        t, p = self._ids(B, track_id, param_id)
+        A = np.empty((B, N, NX, NX))
+        Bm = np.empty((B, N, NU, NX))
+        d = np.empty((B, N, NX))
+        self._check(self._lib.fsae_linearise_host(self._ctx, model, B, N, float(dt), _ip(t), _ip(p),
+                                                  _dp(x_lin), _dp(u_lin), _dp(A), _dp(Bm), _dp(d)),
+                    "fsae_linearise_host")
+        return A.transpose(0, 1, 3, 2), Bm.transpose(0, 1, 3, 2), d
+
+    def condense(self, model, x0, x_ref, dt, x_lin, u_lin, track_id=None, param_id=None):
+        """sequential_integration.m + *_state_constraints.m + generate_qp.m.  Returns a dict of
+        per-problem matrices in natural (row, col) indexing."""
+        NX, NU, NS = _DIMS[model]
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        B = x0.shape[0]
+        N = np.asarray(x_ref).shape[1]
+        x0 = _f64(x0, (B, NX))
+        x_ref = _f64(x_ref, (B, N, NX))
+        x_lin = _f64(x_lin, (B, N, NX))
+        u_lin = _f64(u_lin, (B, N, NU))
+        t, p = self._ids(B, track_id, param_id)
+        nV, nC, nXN = NU * N + NS, (6 if model == KINEMATIC else 20) * N, NX * N
+        o = dict(H=np.empty((B, nV, nV)), f=np.empty((B, nV)), xA=np.empty((B, nV, nC)),
+                 lbA=np.empty((B, nC)), ubA=np.empty((B, nC)), lb=np.empty((B, nV)), ub=np.empty((B, nV)),
+                 A_bar=np.empty((B, NX, nXN)), B_bar=np.empty((B, nV, nXN)), d_bar=np.empty((B, nXN)),
+                 const=np.empty(B))
+        self._check(self._lib.fsae_condense_host(
+            self._ctx, model, B, N, float(dt), _ip(t), _ip(p), _dp(x0), _dp(x_ref), _dp(x_lin), _dp(u_lin),
+            _dp(o["H"]), _dp(o["f"]), _dp(o["xA"]), _dp(o["lbA"]), _dp(o["ubA"]), _dp(o["lb"]), _dp(o["ub"]),
+            _dp(o["A_bar"]), _dp(o["B_bar"]), _dp(o["d_bar"]), _dp(o["const"])), "fsae_condense_host")
+        for k in ("H", "xA", "A_bar", "B_bar"):
+            o[k] = o[k].transpose(0, 2, 1)       # column-major blocks -> (row, col)
+        return o
+
+    # ------------------------------------------------------------------ the fused step
+    def _ltvmpc(self, model, x0, x_ref, dt, x_lin, u_lin, track_id, param_id):
+        NX, NU, NS = _DIMS[model]
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        B = x0.shape[0]
+        N = np.asarray(x_ref).shape[1]
+        x0 = _f64(x0, (B, NX))
+        x_ref = _f64(x_ref, (B, N, NX))
+        x_lin = _f64(x_lin, (B, N, NX))
+        u_lin = _f64(u_lin, (B, N, NU))
+        t, p = self._ids(B, track_id, param_id)
+        nV, nC = NU * N + NS, (6 if model == KINEMATIC else 20) * N
+        r = MpcResult(np.empty((B, NU * N)), np.empty((B, NX * N)), np.empty(B, np.int32), np.empty(B),
+                      np.empty((B, NS)), np.empty(B, np.int32), np.empty((B, nV), np.int8),
+                      np.empty((B, nC), np.int8))
+        self._check(self._lib.fsae_ltvmpc_host(
+            self._ctx, model, B, N, float(dt), _ip(t), _ip(p), _dp(x0), _dp(x_ref), _dp(x_lin), _dp(u_lin),
+            _dp(r.u_opt), _dp(r.x_opt), _ip(r.exitflag), _dp(r.fval), _dp(r.slack_opt), _ip(r.iters),
+            r.workingSetB.ctypes.data_as(C.POINTER(C.c_int8)),
+            r.workingSetC.ctypes.data_as(C.POINTER(C.c_int8))), "fsae_ltvmpc_host")
+        return r
+
+    def ltvmpc_kinetmatic_curvilinear(self, x0, x_ref, dt, x_lin, u_lin, track_id=None, param_id=None):
+        """mpc/ltv/kinematic/ltvmpc_kinetmatic_curvilinear.m:1 (name kept, typo included)."""
+        return self._ltvmpc(KINEMATIC, x0, x_ref, dt, x_lin, u_lin, track_id, param_id)
+
+    def ltvmpc_dynamic_curvilinear(self, x0, x_ref, dt, x_lin, u_lin, track_id=None, param_id=None):
+        """mpc/ltv/dynamic/ltvmpc_dynamic_curvilinear.m:1."""
+        return self._ltvmpc(DYNAMIC, x0, x_ref, dt, x_lin, u_lin, track_id, param_id)
+
+    def ltvmpc_dev(self, model, B, N, dt, ptrs, stream=0):
+        """Device-pointer entry (fsae_ltvmpc_dev).  `ptrs` is a dict of integer device
+        addresses: x0,x_ref,x_lin,u_lin,u_opt,x_opt,exitflag,fval,slack_opt and optionally
+        track_id,param_id,iters,workingSetB,workingSetC.  Never synchronises."""
+        g = lambda k: C.c_void_p(ptrs.get(k) or None)
+        self._check(self._lib.fsae_ltvmpc_dev(
+            self._ctx, model, int(B), int(N), float(dt), g("track_id"), g("param_id"),
+            g("x0"), g("x_ref"), g("x_lin"), g("u_lin"), g("u_opt"), g("x_opt"), g("exitflag"),
+            g("fval"), g("slack_opt"), g("iters"), g("workingSetB"), g("workingSetC"),
+            C.c_void_p(stream or None)), "fsae_ltvmpc_dev")
+
+    # ------------------------------------------------------------------ diagnostics
+    @property
+    def launch_count(self):
+        return int(self._lib.fsae_launch_count(self._ctx))
+
+    @property
+    def last_kernel_ms(self):
+        return float(self._lib.fsae_last_kernel_ms(self._ctx))
+
+    @property
+    def stream(self):
+        return int(self._lib.fsae_stream(self._ctx) or 0)
+
+    def counters(self, reset=False):
+        """(adds, drops, refreshes) summed over all problems solved so far."""
+        out = (C.c_uint64 * 3)()
+        self._check(self._lib.fsae_debug_counters(self._ctx, out, int(reset)), "fsae_debug_counters")
+        return tuple(int(v) for v in out)

@@ -1,0 +1,454 @@
+// C-ABI of fsae_mpc_b200 (see include/fsae_mpc_b200.h).  Host-side plumbing only:
+// context, parameter/track tables, staging buffers, kernel launches.  No CPU compute path.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/fsae_mpc_b200.h"
+#include "fused_v1.cuh"
+#include "staged.cuh"
+
+using namespace fsae;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct fsae_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    std::string err;
+    int64_t launches = 0;
+    fsae_params h_params[FSAE_MAX_PARAM_SETS];
+    fsae_params* d_params = nullptr;
+    DevTrack h_tracks[FSAE_MAX_TRACKS];
+    double* d_coef[FSAE_MAX_TRACKS];
+    DevTrack* d_tracks = nullptr;
+    unsigned long long* d_counters = nullptr;
+    // staging for *_host calls
+    DevBuf in[8], out[12];
+};
+
+#define CK(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);             \
+            return FSAE_ERR_CUDA;                                                      \
+        }                                                                              \
+    } while (0)
+
+extern "C" const char* fsae_version(void) { return "fsae_mpc_b200 0.1 (sm_100a)"; }
+
+extern "C" void fsae_default_params(int model, fsae_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->lr = 0.6183; p->lf = 0.8672; p->mass = 280.0; p->inertia = 200.0; p->grav = 9.81;
+    p->pac_B = 12.56; p->pac_C = 1.38; p->pac_D = 1.60; p->pac_E = -0.58;
+    const double Q[7] = {5, 250, 2000, 0, 0, 0, 0};
+    for (int i = 0; i < 7; ++i) { p->Q[i] = Q[i]; p->Q_terminal[i] = Q[i] * 10; }
+    p->R[0] = 10; p->R[1] = 10;
+    if (model == FSAE_MODEL_DYNAMIC) {
+        p->R_soft[0] = 1e8; p->R_soft[1] = 1e6; p->R_soft[2] = 1e6; p->R_soft[3] = 1e4;
+        p->lin_scheme = FSAE_LIN_RK4;
+    } else {
+        p->R_soft[0] = 1e8;
+        p->lin_scheme = FSAE_LIN_RK2;
+    }
+    p->u_lb[0] = -10; p->u_lb[1] = -0.4; p->u_ub[0] = 10; p->u_ub[1] = 0.4;
+    p->vel_lb = 0; p->vel_ub = INFINITY;
+    p->delta_lb = -0.4; p->delta_ub = 0.4;
+    p->n_lb = -0.75; p->n_ub = 0.75;
+    p->soft_far = 1e10;
+    p->ay_max = 5.0;
+    p->slip_max = 0.1;
+    p->ac_max = 9.163; p->al_max = 10.0;
+    p->max_iter = 1000;
+    p->feas_tol = 1e-9;
+    p->flat_eps = 1e-8;
+}
+
+extern "C" int fsae_create(fsae_ctx** out, int device) {
+    if (!out) return FSAE_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= device || device < 0) return FSAE_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FSAE_ERR_CUDA;
+    if (prop.major != 10) return FSAE_ERR_CUDA;     // built for sm_100a only; no fallback
+    fsae_ctx* ctx = new fsae_ctx();
+    ctx->device = device;
+    memset(ctx->h_tracks, 0, sizeof(ctx->h_tracks));
+    memset(ctx->d_coef, 0, sizeof(ctx->d_coef));
+    auto fail = [&](const char* what) {
+        fprintf(stderr, "fsae_create: %s failed: %s\n", what, cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return FSAE_ERR_CUDA;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice");
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) return fail("event");
+    if (cudaMalloc(&ctx->d_params, sizeof(fsae_params) * FSAE_MAX_PARAM_SETS) != cudaSuccess) return fail("malloc params");
+    if (cudaMalloc(&ctx->d_tracks, sizeof(DevTrack) * FSAE_MAX_TRACKS) != cudaSuccess) return fail("malloc tracks");
+    if (cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) return fail("malloc counters");
+    cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long));
+    cudaMemset(ctx->d_tracks, 0, sizeof(DevTrack) * FSAE_MAX_TRACKS);
+    for (int i = 0; i < FSAE_MAX_PARAM_SETS; ++i) fsae_default_params(FSAE_MODEL_KINEMATIC, &ctx->h_params[i]);
+    if (cudaMemcpy(ctx->d_params, ctx->h_params, sizeof(ctx->h_params), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail("memcpy params");
+    *out = ctx;
+    return FSAE_OK;
+}
+
+extern "C" int fsae_destroy(fsae_ctx* ctx) {
+    if (!ctx) return FSAE_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->in) b.release();
+    for (auto& b : ctx->out) b.release();
+    for (int i = 0; i < FSAE_MAX_TRACKS; ++i)
+        if (ctx->d_coef[i]) cudaFree(ctx->d_coef[i]);
+    cudaFree(ctx->d_params);
+    cudaFree(ctx->d_tracks);
+    cudaFree(ctx->d_counters);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return FSAE_OK;
+}
+
+extern "C" const char* fsae_last_error(const fsae_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+extern "C" int64_t fsae_launch_count(const fsae_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* fsae_stream(const fsae_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" float fsae_last_kernel_ms(const fsae_ctx* ctx) {
+    if (!ctx || !ctx->ev_valid) return 0.f;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return 0.f;
+    return ms;
+}
+
+extern "C" int fsae_set_params(fsae_ctx* ctx, int id, const fsae_params* p) {
+    if (!ctx || !p || id < 0 || id >= FSAE_MAX_PARAM_SETS) return FSAE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ctx->h_params[id] = *p;
+    CK(cudaMemcpyAsync(ctx->d_params + id, &ctx->h_params[id], sizeof(fsae_params), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSAE_OK;
+}
+
+extern "C" int fsae_set_track(fsae_ctx* ctx, int track_id, const double* x_spline, const double* y_spline,
+                              int n_seg, double dl) {
+    if (!ctx || !x_spline || !y_spline || track_id < 0 || track_id >= FSAE_MAX_TRACKS || n_seg <= 0 || !(dl > 0))
+        return FSAE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    // MATLAB [n_seg x 4] column-major  ->  per-segment [x P0..P3 | y P0..P3]
+    std::vector<double> h((size_t)n_seg * 8);
+    for (int i = 0; i < n_seg; ++i)
+        for (int k = 0; k < 4; ++k) {
+            h[(size_t)i * 8 + k] = x_spline[(size_t)k * n_seg + i];
+            h[(size_t)i * 8 + 4 + k] = y_spline[(size_t)k * n_seg + i];
+        }
+    if (ctx->d_coef[track_id]) { cudaFree(ctx->d_coef[track_id]); ctx->d_coef[track_id] = nullptr; }
+    CK(cudaMalloc(&ctx->d_coef[track_id], h.size() * sizeof(double)));
+    CK(cudaMemcpy(ctx->d_coef[track_id], h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->h_tracks[track_id].coef = ctx->d_coef[track_id];
+    ctx->h_tracks[track_id].n_seg = n_seg;
+    ctx->h_tracks[track_id].dl = dl;
+    CK(cudaMemcpy(ctx->d_tracks + track_id, &ctx->h_tracks[track_id], sizeof(DevTrack), cudaMemcpyHostToDevice));
+    return FSAE_OK;
+}
+
+static int check_ids(fsae_ctx* ctx, int B, const int32_t* track_id, const int32_t* param_id) {
+    if (track_id) {
+        for (int i = 0; i < B; ++i)
+            if (track_id[i] < 0 || track_id[i] >= FSAE_MAX_TRACKS || !ctx->h_tracks[track_id[i]].coef) {
+                ctx->err = "track_id refers to a track that was never set";
+                return FSAE_ERR_ARG;
+            }
+    } else if (!ctx->h_tracks[0].coef) {
+        ctx->err = "track 0 not set (fsae_set_track)";
+        return FSAE_ERR_ARG;
+    }
+    if (param_id)
+        for (int i = 0; i < B; ++i)
+            if (param_id[i] < 0 || param_id[i] >= FSAE_MAX_PARAM_SETS) {
+                ctx->err = "param_id out of range";
+                return FSAE_ERR_ARG;
+            }
+    return FSAE_OK;
+}
+
+extern "C" int fsae_interpolate_curvature_host(fsae_ctx* ctx, int track_id, const double* s, int64_t n,
+                                               double* kappa_out) {
+    if (!ctx || !s || !kappa_out || n < 0 || track_id < 0 || track_id >= FSAE_MAX_TRACKS) return FSAE_ERR_ARG;
+    if (!ctx->h_tracks[track_id].coef) { ctx->err = "track not set"; return FSAE_ERR_ARG; }
+    if (n == 0) return FSAE_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->in[0].reserve(n * sizeof(double)));
+    CK(ctx->out[0].reserve(n * sizeof(double)));
+    CK(cudaMemcpyAsync(ctx->in[0].p, s, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    curvature_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->h_tracks[track_id], (const double*)ctx->in[0].p, (long long)n, (double*)ctx->out[0].p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(kappa_out, ctx->out[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSAE_OK;
+}
+
+static int model_dims(int model, int& NX, int& NU, int& NS) {
+    if (model == FSAE_MODEL_KINEMATIC) { NX = 5; NU = 2; NS = 1; return FSAE_OK; }
+    if (model == FSAE_MODEL_DYNAMIC) { NX = 7; NU = 2; NS = 4; return FSAE_OK; }
+    return FSAE_ERR_ARG;
+}
+
+// upload optional id arrays; returns device pointers (or nullptr)
+static int upload_ids(fsae_ctx* ctx, int B, const int32_t* track_id, const int32_t* param_id,
+                      const int32_t** d_tid, const int32_t** d_pid) {
+    *d_tid = nullptr;
+    *d_pid = nullptr;
+    if (track_id) {
+        CK(ctx->in[6].reserve((size_t)B * 4));
+        CK(cudaMemcpyAsync(ctx->in[6].p, track_id, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->stream));
+        *d_tid = (const int32_t*)ctx->in[6].p;
+    }
+    if (param_id) {
+        CK(ctx->in[7].reserve((size_t)B * 4));
+        CK(cudaMemcpyAsync(ctx->in[7].p, param_id, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->stream));
+        *d_pid = (const int32_t*)ctx->in[7].p;
+    }
+    return FSAE_OK;
+}
+
+extern "C" int fsae_linearise_host(fsae_ctx* ctx, int model, int B, int N, double dt,
+                                   const int32_t* track_id, const int32_t* param_id,
+                                   const double* x_lin, const double* u_lin,
+                                   double* A, double* Bm, double* d) {
+    int NX, NU, NS;
+    if (!ctx || model_dims(model, NX, NU, NS) != FSAE_OK || B < 0 || N <= 0 || !x_lin || !u_lin || !A || !Bm || !d)
+        return FSAE_ERR_ARG;
+    if (B == 0) return FSAE_OK;
+    int rc = check_ids(ctx, B, track_id, param_id);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t T = (size_t)B * N;
+    CK(ctx->in[2].reserve(T * NX * 8));
+    CK(ctx->in[3].reserve(T * NU * 8));
+    CK(ctx->out[0].reserve(T * NX * NX * 8));
+    CK(ctx->out[1].reserve(T * NX * NU * 8));
+    CK(ctx->out[2].reserve(T * NX * 8));
+    const int32_t *d_tid, *d_pid;
+    rc = upload_ids(ctx, B, track_id, param_id, &d_tid, &d_pid);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->in[2].p, x_lin, T * NX * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->in[3].p, u_lin, T * NU * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned grid = (unsigned)((T + 127) / 128);
+    if (model == FSAE_MODEL_KINEMATIC)
+        linearise_kernel<KinModel><<<grid, 128, 0, ctx->stream>>>(B, N, dt, d_tid, d_pid, ctx->d_tracks, ctx->d_params,
+            (const double*)ctx->in[2].p, (const double*)ctx->in[3].p, (double*)ctx->out[0].p, (double*)ctx->out[1].p, (double*)ctx->out[2].p);
+    else
+        linearise_kernel<DynModel><<<grid, 128, 0, ctx->stream>>>(B, N, dt, d_tid, d_pid, ctx->d_tracks, ctx->d_params,
+            (const double*)ctx->in[2].p, (const double*)ctx->in[3].p, (double*)ctx->out[0].p, (double*)ctx->out[1].p, (double*)ctx->out[2].p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(A, ctx->out[0].p, T * NX * NX * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(Bm, ctx->out[1].p, T * NX * NU * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(d, ctx->out[2].p, T * NX * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSAE_OK;
+}
+
+extern "C" int fsae_condense_host(fsae_ctx* ctx, int model, int B, int N, double dt,
+                                  const int32_t* track_id, const int32_t* param_id,
+                                  const double* x0, const double* x_ref,
+                                  const double* x_lin, const double* u_lin,
+                                  double* H, double* f, double* xA, double* lbA, double* ubA,
+                                  double* lb, double* ub,
+                                  double* A_bar, double* B_bar, double* d_bar, double* cost_const) {
+    int NX, NU, NS;
+    if (!ctx || model_dims(model, NX, NU, NS) != FSAE_OK || B < 0 || N <= 0 || N > 80 || !x0 || !x_ref || !x_lin || !u_lin)
+        return FSAE_ERR_ARG;
+    if (model != FSAE_MODEL_KINEMATIC) { ctx->err = "condense: dynamic model not built yet"; return FSAE_ERR_UNSUPPORTED; }
+    if (B == 0) return FSAE_OK;
+    int rc = check_ids(ctx, B, track_id, param_id);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int nU = NU * N, nV = nU + NS, nXN = NX * N;
+    const int nC = (model == FSAE_MODEL_KINEMATIC) ? 6 * N : 20 * N;
+    const size_t sz_in[4] = {(size_t)B * NX * 8, (size_t)B * nXN * 8, (size_t)B * nXN * 8, (size_t)B * nU * 8};
+    const double* src[4] = {x0, x_ref, x_lin, u_lin};
+    for (int i = 0; i < 4; ++i) {
+        CK(ctx->in[i].reserve(sz_in[i]));
+        CK(cudaMemcpyAsync(ctx->in[i].p, src[i], sz_in[i], cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int32_t *d_tid, *d_pid;
+    rc = upload_ids(ctx, B, track_id, param_id, &d_tid, &d_pid);
+    if (rc) return rc;
+    const size_t sz_out[11] = {(size_t)B * nV * nV * 8, (size_t)B * nV * 8, (size_t)B * nC * nV * 8,
+                               (size_t)B * nC * 8, (size_t)B * nC * 8, (size_t)B * nV * 8, (size_t)B * nV * 8,
+                               (size_t)B * nXN * NX * 8, (size_t)B * nXN * nV * 8, (size_t)B * nXN * 8, (size_t)B * 8};
+    double* dst[11] = {H, f, xA, lbA, ubA, lb, ub, A_bar, B_bar, d_bar, cost_const};
+    for (int i = 0; i < 11; ++i) CK(ctx->out[i].reserve(sz_out[i]));
+    CondenseArgs a;
+    a.B = B; a.N = N; a.dt = dt; a.track_id = d_tid; a.param_id = d_pid;
+    a.tracks = ctx->d_tracks; a.params = ctx->d_params;
+    a.x0 = (const double*)ctx->in[0].p; a.x_ref = (const double*)ctx->in[1].p;
+    a.x_lin = (const double*)ctx->in[2].p; a.u_lin = (const double*)ctx->in[3].p;
+    a.H = H ? (double*)ctx->out[0].p : nullptr;
+    a.f = f ? (double*)ctx->out[1].p : nullptr;
+    a.xA = xA ? (double*)ctx->out[2].p : nullptr;
+    a.lbA = (lbA && ubA) ? (double*)ctx->out[3].p : nullptr;
+    a.ubA = (lbA && ubA) ? (double*)ctx->out[4].p : nullptr;
+    a.lb = (lb && ub) ? (double*)ctx->out[5].p : nullptr;
+    a.ub = (lb && ub) ? (double*)ctx->out[6].p : nullptr;
+    a.A_bar = (double*)ctx->out[7].p; a.B_bar = (double*)ctx->out[8].p; a.d_bar = (double*)ctx->out[9].p;
+    a.cconst = cost_const ? (double*)ctx->out[10].p : nullptr;
+    condense_kernel<KinModel, 80><<<B, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    for (int i = 0; i < 11; ++i)
+        if (dst[i]) CK(cudaMemcpyAsync(dst[i], ctx->out[i].p, sz_out[i], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSAE_OK;
+}
+
+// ------------------------------------------------------------------ fused step
+template <class Model, int N, int NT>
+static int launch_fused_v1(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
+    using S_t = SmemV1<Model, N, NT>;
+    auto kern = ltvmpc_fused_v1_kernel<Model, N, NT>;
+    static bool configured[64] = {false};
+    if (!configured[ctx->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S_t)));
+        configured[ctx->device & 63] = true;
+    }
+    kern<<<a.B, NT, sizeof(S_t), st>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return FSAE_OK;
+}
+
+extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt,
+                               const int32_t* track_id, const int32_t* param_id,
+                               const double* x0, const double* x_ref,
+                               const double* x_lin, const double* u_lin,
+                               double* u_opt, double* x_opt, int32_t* exitflag, double* fval,
+                               double* slack_opt, int32_t* iters,
+                               int8_t* workingSetB, int8_t* workingSetC, void* stream) {
+    int NX, NU, NS;
+    if (!ctx || model_dims(model, NX, NU, NS) != FSAE_OK || B < 0 || !x0 || !x_ref || !x_lin || !u_lin ||
+        !u_opt || !x_opt || !exitflag || !fval || !slack_opt)
+        return FSAE_ERR_ARG;
+    if (B == 0) return FSAE_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    BatchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.N = N; a.dt = dt; a.track_id = track_id; a.param_id = param_id;
+    a.x0 = x0; a.x_ref = x_ref; a.x_lin = x_lin; a.u_lin = u_lin;
+    a.u_opt = u_opt; a.x_opt = x_opt; a.exitflag = exitflag; a.fval = fval; a.slack_opt = slack_opt;
+    a.iters = iters; a.wsB = workingSetB; a.wsC = workingSetC;
+    a.tracks = ctx->d_tracks; a.params = ctx->d_params;
+    a.counters = ctx->d_counters;
+    CK(cudaEventRecord(ctx->ev0, st));
+    int rc = FSAE_ERR_UNSUPPORTED;
+    if (model == FSAE_MODEL_KINEMATIC) {
+        if (N == 40) rc = launch_fused_v1<KinModel, 40, 256>(ctx, a, st);
+        else if (N == 20) rc = launch_fused_v1<KinModel, 20, 256>(ctx, a, st);
+        else ctx->err = "kinematic fused step: horizon must be 20 or 40";
+    } else {
+        ctx->err = "dynamic fused step not built yet";
+    }
+    if (rc != FSAE_OK) return rc;
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->ev_valid = true;
+    return FSAE_OK;
+}
+
+extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double dt,
+                                const int32_t* track_id, const int32_t* param_id,
+                                const double* x0, const double* x_ref,
+                                const double* x_lin, const double* u_lin,
+                                double* u_opt, double* x_opt, int32_t* exitflag, double* fval,
+                                double* slack_opt, int32_t* iters,
+                                int8_t* workingSetB, int8_t* workingSetC) {
+    int NX, NU, NS;
+    if (!ctx || model_dims(model, NX, NU, NS) != FSAE_OK || B < 0 || !x0 || !x_ref || !x_lin || !u_lin ||
+        !u_opt || !x_opt || !exitflag || !fval || !slack_opt)
+        return FSAE_ERR_ARG;
+    if (B == 0) return FSAE_OK;
+    int rc = check_ids(ctx, B, track_id, param_id);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int nU = NU * N, nV = nU + NS, nXN = NX * N;
+    const int nC = (model == FSAE_MODEL_KINEMATIC) ? 6 * N : 20 * N;
+    const size_t sz_in[4] = {(size_t)B * NX * 8, (size_t)B * nXN * 8, (size_t)B * nXN * 8, (size_t)B * nU * 8};
+    const double* src[4] = {x0, x_ref, x_lin, u_lin};
+    for (int i = 0; i < 4; ++i) {
+        CK(ctx->in[i].reserve(sz_in[i]));
+        CK(cudaMemcpyAsync(ctx->in[i].p, src[i], sz_in[i], cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int32_t *d_tid, *d_pid;
+    rc = upload_ids(ctx, B, track_id, param_id, &d_tid, &d_pid);
+    if (rc) return rc;
+    const size_t sz_out[8] = {(size_t)B * nU * 8, (size_t)B * nXN * 8, (size_t)B * 4, (size_t)B * 8,
+                              (size_t)B * NS * 8, (size_t)B * 4, (size_t)B * nV, (size_t)B * nC};
+    void* dst[8] = {u_opt, x_opt, exitflag, fval, slack_opt, iters, workingSetB, workingSetC};
+    for (int i = 0; i < 8; ++i) CK(ctx->out[i].reserve(sz_out[i]));
+    rc = fsae_ltvmpc_dev(ctx, model, B, N, dt, d_tid, d_pid,
+                         (const double*)ctx->in[0].p, (const double*)ctx->in[1].p,
+                         (const double*)ctx->in[2].p, (const double*)ctx->in[3].p,
+                         (double*)ctx->out[0].p, (double*)ctx->out[1].p, (int32_t*)ctx->out[2].p,
+                         (double*)ctx->out[3].p, (double*)ctx->out[4].p,
+                         iters ? (int32_t*)ctx->out[5].p : nullptr,
+                         workingSetB ? (int8_t*)ctx->out[6].p : nullptr,
+                         workingSetC ? (int8_t*)ctx->out[7].p : nullptr, ctx->stream);
+    if (rc) return rc;
+    for (int i = 0; i < 8; ++i)
+        if (dst[i]) CK(cudaMemcpyAsync(dst[i], ctx->out[i].p, sz_out[i], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSAE_OK;
+}
+
+extern "C" int fsae_qpoases_host(fsae_ctx* ctx, int B, int nV, int nC,
+                                 const double* H, const double* g, const double* A,
+                                 const double* lb, const double* ub, const double* lbA, const double* ubA,
+                                 double* x, double* fval, int32_t* exitflag, int32_t* iters,
+                                 double* lambda, int8_t* workingSetB, int8_t* workingSetC) {
+    if (!ctx) return FSAE_ERR_ARG;
+    ctx->err = "dense qpOASES drop-in not built yet";
+    return FSAE_ERR_UNSUPPORTED;
+}
+
+// debug / test taps -------------------------------------------------------------------
+extern "C" int fsae_debug_counters(fsae_ctx* ctx, uint64_t* out3, int reset) {
+    if (!ctx || !out3) return FSAE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    unsigned long long h[3];
+    CK(cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 3; ++i) out3[i] = h[i];
+    if (reset) CK(cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
+    return FSAE_OK;
+}

@@ -1,0 +1,144 @@
+"""GPU parity tests (through the C-ABI) of the kinematic LTV-MPC path against the oracle
+and the committed golden fixtures.  Tolerance: north_star's |du|inf <= 1e-6 relative, and
+the same active set; the intermediate (pre-QP) stages are held to 1e-9 relative."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, c_layout, DT
+
+pytestmark = pytest.mark.gpu
+
+U_RTOL = 1e-6
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b)))
+
+
+def test_curvature_matches_oracle(mpc, fsg):
+    s = np.concatenate([np.linspace(-50, 700, 4001), [0.0, fsg.L, fsg.dl, 2 * fsg.L - 1e-9]])
+    k_gpu = mpc.interpolate_curvature(s, 0)
+    k_ref = fsg.kappa(s)
+    assert np.max(np.abs(k_gpu - k_ref)) <= 1e-12 * max(1.0, np.max(np.abs(k_ref)))
+
+
+@pytest.mark.parametrize("scheme", [1, 2, 4])
+def test_linearise_matches_oracle(mpc, fsg, scheme):
+    import fsae_mpc_b200 as fm
+    from oracle import ltv
+    g = load_golden("kinematic_lap_fsg2019.npz")
+    p = fm.default_params(fm.KINEMATIC)
+    p.lin_scheme = scheme
+    mpc.set_params(1, p)
+    B = min(8, g["x_lin"].shape[0])
+    pid = np.ones(B, np.int32)
+    A, Bm, d = mpc.linearise(fm.KINEMATIC, c_layout(g["x_lin"][:B]), c_layout(g["u_lin"][:B]), DT, param_id=pid)
+    fn = {1: ltv.euler_kinematic_curvilinear, 2: ltv.rk2_kinematic_curvilinear, 4: ltv.rk4_kinematic_curvilinear}[scheme]
+    for b in range(B):
+        Ao, Bo, do = fn(g["x_lin"][b], g["u_lin"][b], fsg.kappa, DT)
+        assert rel(A[b], Ao.transpose(2, 0, 1)) < 1e-11
+        assert rel(Bm[b], Bo.transpose(2, 0, 1)) < 1e-11
+        assert rel(d[b], do.T) < 1e-11
+
+
+def test_condense_matches_golden_stage(mpc):
+    import fsae_mpc_b200 as fm
+    g = load_golden("kinematic_lap_fsg2019.npz")
+    idx = g["stage_idx"]
+    o = mpc.condense(fm.KINEMATIC, g["x0"][idx], c_layout(g["x_ref"][idx]), DT,
+                     c_layout(g["x_lin"][idx]), c_layout(g["u_lin"][idx]))
+    for k in ("A_bar", "B_bar", "d_bar", "H", "f", "xA", "const"):
+        assert rel(o[k], g["stage_" + k]) < 1e-10, k
+    for k in ("lbA", "ubA", "lb", "ub"):
+        a, b = o[k], g["stage_" + k]
+        assert np.array_equal(np.isinf(a), np.isinf(b)), k
+        fin = np.isfinite(b)
+        assert np.array_equal(np.sign(a[~fin]), np.sign(b[~fin])), k
+        assert np.max(np.abs(a[fin] - b[fin]) / (1 + np.abs(b[fin]))) < 1e-10, k
+
+
+def _check_solution(r, g, sl=slice(None)):
+    assert np.array_equal(r.exitflag, g["exitflag"][sl].astype(np.int32))
+    scale = np.maximum(1.0, np.max(np.abs(g["u_opt"][sl]), axis=1))
+    du = np.max(np.abs(r.u_opt - g["u_opt"][sl]), axis=1) / scale
+    assert du.max() <= U_RTOL, f"max |du|inf rel = {du.max():.3e} at {du.argmax()}"
+    xs = np.maximum(1.0, np.max(np.abs(g["x_opt"][sl]), axis=1))
+    assert (np.max(np.abs(r.x_opt - g["x_opt"][sl]), axis=1) / xs).max() <= U_RTOL
+    assert np.max(np.abs(r.fval - g["fval"][sl]) / (1 + np.abs(g["fval"][sl]))) <= 1e-7
+    assert np.max(np.abs(r.slack_opt - g["slack"][sl])) <= 1e-7
+    # same active set (non-degenerate problems): compare working sets exactly
+    same_B = (r.workingSetB == g["wsB"][sl]).all(axis=1)
+    same_C = (r.workingSetC == g["wsC"][sl]).all(axis=1)
+    assert (same_B & same_C).mean() >= 0.98, f"working set differs on {(~(same_B & same_C)).sum()} problems"
+
+
+def test_fused_step_matches_golden_lap(mpc):
+    g = load_golden("kinematic_lap_fsg2019.npz")
+    r = mpc.ltvmpc_kinetmatic_curvilinear(g["x0"], c_layout(g["x_ref"]), DT, c_layout(g["x_lin"]), c_layout(g["u_lin"]))
+    _check_solution(r, g)
+
+
+def test_fused_step_matches_golden_perturbed(mpc):
+    g = load_golden("kinematic_perturbed_fsg2019.npz")
+    r = mpc.ltvmpc_kinetmatic_curvilinear(g["x0"], c_layout(g["x_ref"]), DT, c_layout(g["x_lin"]), c_layout(g["u_lin"]))
+    _check_solution(r, g)
+
+
+def test_fused_step_other_track(mpc):
+    g = load_golden("kinematic_lap_fso2020.npz")
+    B = g["x0"].shape[0]
+    r = mpc.ltvmpc_kinetmatic_curvilinear(g["x0"], c_layout(g["x_ref"]), DT, c_layout(g["x_lin"]), c_layout(g["u_lin"]),
+                                          track_id=np.full(B, 2, np.int32))
+    _check_solution(r, g)
+
+
+def test_fused_step_live_oracle(mpc, fsg):
+    """Fresh random perturbations solved by the oracle at test time (no fixture)."""
+    from oracle import ltv
+    g = load_golden("kinematic_lap_fsg2019.npz")
+    rng = np.random.default_rng(123)
+    B = 12
+    pick = rng.integers(g["x0"].shape[0], size=B)
+    x0 = g["x0"][pick].copy()
+    x0[:, 1] += rng.uniform(-0.2, 0.2, B)
+    x0[:, 3] = np.maximum(0.5, x0[:, 3] + rng.uniform(-1, 1, B))
+    r = mpc.ltvmpc_kinetmatic_curvilinear(x0, c_layout(g["x_ref"][pick]), DT, c_layout(g["x_lin"][pick]),
+                                          c_layout(g["u_lin"][pick]))
+    for b in range(B):
+        u, x, ef, fv, sl, sol = ltv.ltvmpc_kinetmatic_curvilinear(x0[b], g["x_ref"][pick[b]], fsg.kappa, DT,
+                                                                   g["x_lin"][pick[b]], g["u_lin"][pick[b]])
+        assert ef == r.exitflag[b] == 0
+        assert rel(r.u_opt[b], u) <= U_RTOL
+        assert rel(r.x_opt[b], x) <= U_RTOL
+
+
+def test_batch_edge_cases(mpc):
+    import fsae_mpc_b200 as fm
+    g = load_golden("kinematic_lap_fsg2019.npz")
+    # empty batch
+    r = mpc.ltvmpc_kinetmatic_curvilinear(np.zeros((0, 5)), np.zeros((0, 40, 5)), DT, np.zeros((0, 40, 5)), np.zeros((0, 40, 2)))
+    assert r.u_opt.shape == (0, 80)
+    # single problem and a ragged (non multiple of anything) batch give identical per-problem results
+    xr, xl, ul = c_layout(g["x_ref"]), c_layout(g["x_lin"]), c_layout(g["u_lin"])
+    r1 = mpc.ltvmpc_kinetmatic_curvilinear(g["x0"][:1], xr[:1], DT, xl[:1], ul[:1])
+    r7 = mpc.ltvmpc_kinetmatic_curvilinear(g["x0"][:7], xr[:7], DT, xl[:7], ul[:7])
+    assert np.array_equal(r1.u_opt[0], r7.u_opt[0])
+    # unsupported horizon is an error, not a silent fallback
+    with pytest.raises(fm.FsaeError):
+        mpc.ltvmpc_kinetmatic_curvilinear(g["x0"][:1], xr[:1, :33], DT, xl[:1, :33], ul[:1, :33])
+
+
+def test_closed_loop_lap_matches_oracle_prefix(mpc, fsg):
+    """main.m closed loop with the CUDA step in the loop vs the oracle step: the first 60
+    steps of the lap must stay on the same trajectory."""
+    from oracle import closed_loop as cl
+
+    def gpu_step(x0, x_ref, kappa, dt, x_lin, u_lin):
+        r = mpc.ltvmpc_kinetmatic_curvilinear(x0[None], c_layout(x_ref[None]), dt, c_layout(x_lin[None]), c_layout(u_lin[None]))
+        return r.u_opt[0], r.x_opt[0], int(r.exitflag[0]), float(r.fval[0]), r.slack_opt[0]
+
+    h_gpu = cl.run(fsg.track, "KINEMATIC", n_sim=60, mpc_step=gpu_step)
+    h_ref = cl.run(fsg.track, "KINEMATIC", n_sim=60)
+    assert h_gpu["steps"] == h_ref["steps"]
+    assert np.max(np.abs(np.array(h_gpu["x"]) - np.array(h_ref["x"]))) < 1e-6
+    assert all(e == 0 for e in h_gpu["exitflag"])
