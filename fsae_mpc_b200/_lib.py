@@ -62,6 +62,8 @@ SIGNATURES = {
                                   C.c_void_p]),
     "fsae_qpoases_host": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int] + [_dp] * 7
                           + [_dp, _dp, _ip, _ip, _dp, _bp, _bp]),
+    "fsae_debug_counters": (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.c_int]),
+    "fsae_probe_fp64_tflops": (C.c_int, [_ctx, C.POINTER(C.c_double)]),
 }
 
 _lib = None
@@ -81,7 +83,5 @@ def load():
         fn = getattr(lib, name)      # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    lib.fsae_debug_counters.restype = C.c_int
-    lib.fsae_debug_counters.argtypes = [_ctx, C.POINTER(C.c_uint64), C.c_int]
     _lib = lib
     return lib

@@ -226,6 +226,11 @@ class FsaeMpc:
     def stream(self):
         return int(self._lib.fsae_stream(self._ctx) or 0)
 
+    def probe_fp64_tflops(self):
+        out = C.c_double()
+        self._check(self._lib.fsae_probe_fp64_tflops(self._ctx, C.byref(out)), "fsae_probe_fp64_tflops")
+        return float(out.value)
+
     def counters(self, reset=False):
         """(adds, drops, refreshes) summed over all problems solved so far."""
         out = (C.c_uint64 * 3)()

@@ -10,6 +10,7 @@
 #include "../../include/fsae_mpc_b200.h"
 #include "fused_v1.cuh"
 #include "staged.cuh"
+#include "probe.cuh"
 
 using namespace fsae;
 
@@ -450,5 +451,33 @@ extern "C" int fsae_debug_counters(fsae_ctx* ctx, uint64_t* out3, int reset) {
     CK(cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 3; ++i) out3[i] = h[i];
     if (reset) CK(cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
+    return FSAE_OK;
+}
+
+// measured FP64 FMA peak (TFLOP/s, FMA = 2 flops) of the device: roofline denominator
+extern "C" int fsae_probe_fp64_tflops(fsae_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return FSAE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    constexpr int ILP = 8;
+    const int iters = 1 << 14;
+    const int blocks = prop.multiProcessorCount * 8;
+    CK(ctx->out[0].reserve((size_t)blocks * 256 * 8));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        dfma_probe_kernel<ILP><<<blocks, 256, 0, ctx->stream>>>((double*)ctx->out[0].p, iters, 1.0000001, 1e-9);
+        ctx->launches++;
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double flops = 2.0 * ILP * (double)iters * blocks * 256.0;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    ctx->ev_valid = false;
+    *tflops = best;
     return FSAE_OK;
 }

@@ -166,6 +166,14 @@ int fsae_qpoases_host(fsae_ctx* ctx, int B, int nV, int nC,
                       double* x, double* fval, int32_t* exitflag, int32_t* iters,
                       double* lambda, int8_t* workingSetB, int8_t* workingSetC);
 
+/* ---- measurement helpers (bench.py) -------------------------------------------------
+ * Sum over all problems solved on ctx so far of the active-set events
+ * out3 = {constraints added, constraints dropped, refresh steps}; reset != 0 clears them. */
+int fsae_debug_counters(fsae_ctx* ctx, uint64_t* out3, int reset);
+/* Measured FP64 FMA peak of the device in TFLOP/s (FMA = 2 flops): the roofline
+ * denominator for the solve kernel, which MEASURED_PEAKS.json does not carry. */
+int fsae_probe_fp64_tflops(fsae_ctx* ctx, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif
