@@ -183,10 +183,12 @@ def run_ours(args, rank, local_rank, world):
                 u_opt=d_out["u_opt"].data_ptr(), x_opt=d_out["x_opt"].data_ptr(),
                 exitflag=d_out["exitflag"].data_ptr(), fval=d_out["fval"].data_ptr(),
                 slack_opt=d_out["slack"].data_ptr(), iters=d_out["iters"].data_ptr())
-    stream = torch.cuda.current_stream(dev)
+    # all timed work runs on the context's own (non-default) stream; torch events are recorded
+    # on that same stream through an ExternalStream handle
+    stream = torch.cuda.ExternalStream(mpc.stream, device=dev)
 
     def step_dev():
-        mpc.ltvmpc_dev(fm.KINEMATIC, B, N, DT, ptrs, stream=stream.cuda_stream)
+        mpc.ltvmpc_dev(fm.KINEMATIC, B, N, DT, ptrs, stream=mpc.stream)
 
     def barrier():
         if dist is not None:
@@ -217,8 +219,7 @@ def run_ours(args, rank, local_rank, world):
     iters_mean = float(d_out["iters"].double().mean().item())
 
     # ---------------- end-to-end leg: host buffers through the C-ABI host call ----------------
-    ext = torch.cuda.ExternalStream(mpc.stream, device=dev)
-    np_in = [t.numpy() for t in h_in]
+    ext = stream
     lib = mpc._lib
     import ctypes as C
     dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
@@ -320,7 +321,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.ref_sample is None:
-        args.ref_sample = 2048 if args.impl == "reference" else 1024
+        args.ref_sample = 16384 if args.impl == "reference" else 32768
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -63,6 +63,7 @@ SIGNATURES = {
     "fsae_qpoases_host": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int] + [_dp] * 7
                           + [_dp, _dp, _ip, _ip, _dp, _bp, _bp]),
     "fsae_debug_counters": (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.c_int]),
+    "fsae_debug_set_kernel_version": (C.c_int, [_ctx, C.c_int]),
     "fsae_probe_fp64_tflops": (C.c_int, [_ctx, C.POINTER(C.c_double)]),
 }
 

@@ -226,6 +226,10 @@ class FsaeMpc:
     def stream(self):
         return int(self._lib.fsae_stream(self._ctx) or 0)
 
+    def set_kernel_version(self, v):
+        """2 = register-tiled product kernel (default), 1 = shared-memory cross-check variant."""
+        return int(self._lib.fsae_debug_set_kernel_version(self._ctx, int(v)))
+
     def probe_fp64_tflops(self):
         out = C.c_double()
         self._check(self._lib.fsae_probe_fp64_tflops(self._ctx, C.byref(out)), "fsae_probe_fp64_tflops")

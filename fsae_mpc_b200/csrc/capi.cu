@@ -9,6 +9,7 @@
 
 #include "../../include/fsae_mpc_b200.h"
 #include "fused_v1.cuh"
+#include "fused_v2.cuh"
 #include "staged.cuh"
 #include "probe.cuh"
 
@@ -40,6 +41,7 @@ struct fsae_ctx {
     bool ev_valid = false;
     std::string err;
     int64_t launches = 0;
+    int kernel_version = 2;     // 1 = shared-memory operator (cross-check), 2 = register-tiled
     fsae_params h_params[FSAE_MAX_PARAM_SETS];
     fsae_params* d_params = nullptr;
     DevTrack h_tracks[FSAE_MAX_TRACKS];
@@ -350,6 +352,21 @@ static int launch_fused_v1(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
     return FSAE_OK;
 }
 
+template <class Model, int N>
+static int launch_fused_v2(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
+    using S_t = SmemV2<Model, N>;
+    auto kern = ltvmpc_fused_v2_kernel<Model, N>;
+    static bool configured[64] = {false};
+    if (!configured[ctx->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S_t)));
+        configured[ctx->device & 63] = true;
+    }
+    kern<<<a.B, 256, sizeof(S_t), st>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return FSAE_OK;
+}
+
 extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt,
                                const int32_t* track_id, const int32_t* param_id,
                                const double* x0, const double* x_ref,
@@ -375,8 +392,9 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
     CK(cudaEventRecord(ctx->ev0, st));
     int rc = FSAE_ERR_UNSUPPORTED;
     if (model == FSAE_MODEL_KINEMATIC) {
-        if (N == 40) rc = launch_fused_v1<KinModel, 40, 256>(ctx, a, st);
-        else if (N == 20) rc = launch_fused_v1<KinModel, 20, 256>(ctx, a, st);
+        const bool v1 = ctx->kernel_version == 1;
+        if (N == 40) rc = v1 ? launch_fused_v1<KinModel, 40, 256>(ctx, a, st) : launch_fused_v2<KinModel, 40>(ctx, a, st);
+        else if (N == 20) rc = v1 ? launch_fused_v1<KinModel, 20, 256>(ctx, a, st) : launch_fused_v2<KinModel, 20>(ctx, a, st);
         else ctx->err = "kinematic fused step: horizon must be 20 or 40";
     } else {
         ctx->err = "dynamic fused step not built yet";
@@ -480,4 +498,12 @@ extern "C" int fsae_probe_fp64_tflops(fsae_ctx* ctx, double* tflops) {
     ctx->ev_valid = false;
     *tflops = best;
     return FSAE_OK;
+}
+
+// select the fused kernel variant (tests cross-check v1 against v2); returns the previous one
+extern "C" int fsae_debug_set_kernel_version(fsae_ctx* ctx, int v) {
+    if (!ctx || (v != 1 && v != 2)) return FSAE_ERR_ARG;
+    const int old = ctx->kernel_version;
+    ctx->kernel_version = v;
+    return old;
 }

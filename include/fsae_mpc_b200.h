@@ -170,6 +170,9 @@ int fsae_qpoases_host(fsae_ctx* ctx, int B, int nV, int nC,
  * Sum over all problems solved on ctx so far of the active-set events
  * out3 = {constraints added, constraints dropped, refresh steps}; reset != 0 clears them. */
 int fsae_debug_counters(fsae_ctx* ctx, uint64_t* out3, int reset);
+/* Select the fused kernel variant: 2 (default) = register-tiled product kernel,
+ * 1 = shared-memory variant kept as an in-library cross-check.  Returns the previous value. */
+int fsae_debug_set_kernel_version(fsae_ctx* ctx, int version);
 /* Measured FP64 FMA peak of the device in TFLOP/s (FMA = 2 flops): the roofline
  * denominator for the solve kernel, which MEASURED_PEAKS.json does not carry. */
 int fsae_probe_fp64_tflops(fsae_ctx* ctx, double* tflops);

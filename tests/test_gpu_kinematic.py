@@ -142,3 +142,23 @@ def test_closed_loop_lap_matches_oracle_prefix(mpc, fsg):
     assert h_gpu["steps"] == h_ref["steps"]
     assert np.max(np.abs(np.array(h_gpu["x"]) - np.array(h_ref["x"]))) < 1e-6
     assert all(e == 0 for e in h_gpu["exitflag"])
+
+
+def test_kernel_variants_agree(mpc):
+    """v2 (register-tiled product kernel) against v1 (shared-memory variant) on a larger,
+    harder perturbed batch: same exit flags, same solutions."""
+    from fsae_mpc_b200 import workload as wl
+    x0, xr, xl, ul = wl.perturbed_batch("kinematic", "fsg2019", 2048, seed=7)
+    r2 = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
+    old = mpc.set_kernel_version(1)
+    try:
+        r1 = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
+    finally:
+        mpc.set_kernel_version(old)
+    assert (r2.exitflag == 0).all() and (r1.exitflag == 0).all()
+    scale = np.maximum(1.0, np.abs(r1.u_opt).max(axis=1))
+    assert (np.abs(r2.u_opt - r1.u_opt).max(axis=1) / scale).max() < 1e-8
+    assert np.abs(r2.x_opt - r1.x_opt).max() < 1e-7
+    assert np.abs(r2.slack_opt - r1.slack_opt).max() < 1e-9
+    same = (r1.workingSetB == r2.workingSetB).all(axis=1) & (r1.workingSetC == r2.workingSetC).all(axis=1)
+    assert same.mean() > 0.99
