@@ -57,6 +57,7 @@ struct SmemV2 {
     double nvec[G::RP];                // per-warp rows of the normal of the constraint being added
     double zrow[G::RP];                // per-warp reduced z
     double wpart[3][G::RP];            // symv partials
+    double dvec[G::RP];                // LDL' pivots
     double xs[C::NXS * N];
     double dd[N * D::NX];
     double red_val[2][G::NW];
@@ -407,9 +408,6 @@ __global__ void __launch_bounds__(256, 2) ltvmpc_fused_v2_kernel(BatchArgs a) {
     // after step k, rows <= k of columns > k hold J_unit = (L1^-T) entries, the trailing
     // block holds the (full, symmetric) Schur complement.  One column broadcast + one
     // barrier per step; afterwards scale columns by d^-1/2:  J = L^-T, J J' = H_uu^-1.
-    double dcol[CS];                       // pivots of this lane's columns
-#pragma unroll
-    for (int s = 0; s < CS; ++s) dcol[s] = 1.0;
     for (int k = 0; k < nU; ++k) {
         const int ks = k >> 5, kl = k & 31, buf = k & 1;
         if (lane == kl) {
@@ -423,22 +421,38 @@ __global__ void __launch_bounds__(256, 2) ltvmpc_fused_v2_kernel(BatchArgs a) {
         __syncthreads();
         const double piv = S.colk[buf][k];
         const double rp = 1.0 / piv;
-        double vr[RPW];
-#pragma unroll
-        for (int r = 0; r < RPW; ++r) vr[r] = S.colk[buf][row0 + r];
+        if (tid == 0) S.dvec[k] = piv;
+        double lj[CS];
 #pragma unroll
         for (int s = 0; s < CS; ++s) {
             const int j = lane + 32 * s;
-            if (j == k) dcol[s] = piv;
-            if (j > k && j < nU) {
-                const double lj = S.colk[buf][j] * rp;       // symmetric: W[k][j] = W[j][k]
-#pragma unroll
-                for (int r = 0; r < RPW; ++r) {
-                    const int i = row0 + r;
-                    m[r][s] = (i == k) ? -lj : m[r][s] - vr[r] * lj;
-                }
-            }
+            lj[s] = (j > k && j < nU) ? S.colk[buf][j] * rp : 0.0;     // symmetric: W[k][j] = W[j][k]
         }
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const double vr = S.colk[buf][row0 + r];
+#pragma unroll
+            for (int s = 0; s < CS; ++s) m[r][s] = fma(-vr, lj[s], m[r][s]);
+        }
+        const int kr = k - row0;                    // warp-uniform: does this warp own the pivot row?
+        if (kr >= 0 && kr < RPW) {
+#pragma unroll
+            for (int r = 0; r < RPW; ++r)
+                if (r == kr) {
+#pragma unroll
+                    for (int s = 0; s < CS; ++s) {
+                        const int j = lane + 32 * s;
+                        if (j > k && j < nU) m[r][s] = -lj[s];
+                    }
+                }
+        }
+    }
+    __syncthreads();
+    double dcol[CS];                       // pivots of this lane's columns
+#pragma unroll
+    for (int s = 0; s < CS; ++s) {
+        const int j = lane + 32 * s;
+        dcol[s] = (j < nU) ? S.dvec[j] : 1.0;
     }
     // scale, clear the dead lower part, lay out M = [K1 (slack unit columns) | J2]:
     // column c of M:  c < NS -> e_{nU+c};  c >= NS -> J column (c - NS).  The tile holds J in
@@ -736,11 +750,13 @@ __global__ void __launch_bounds__(256, 2) ltvmpc_fused_v2_kernel(BatchArgs a) {
                 }
             }
             d2 = warp_sum(d2);
+            {
+                double tm = t1;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ot = __shfl_xor_sync(0xffffffffu, t1, o);
-                const int ol = __shfl_xor_sync(0xffffffffu, l, o);
-                if (ot < t1 || (ot == t1 && ol >= 0 && (l < 0 || ol < l))) { t1 = ot; l = ol; }
+                for (int o = 16; o > 0; o >>= 1) tm = fmin(tm, __shfl_xor_sync(0xffffffffu, tm, o));
+                const unsigned who = __ballot_sync(0xffffffffu, l >= 0 && t1 == tm);
+                if (who) l = __shfl_sync(0xffffffffu, l, __ffs(who) - 1);
+                t1 = tm;
             }
             const bool lin_dep = !(d2 > 1e-13 * fmax(1.0, nn));
             const double t2 = lin_dep ? INFINITY : (sp < 0.0 ? -sp / d2 : 0.0);
@@ -780,17 +796,23 @@ __global__ void __launch_bounds__(256, 2) ltvmpc_fused_v2_kernel(BatchArgs a) {
                 const double sgd = (yq >= 0.0) ? delta : -delta;
                 const double beta = 1.0 / (d2 + fabs(yq) * delta);
                 const double inv_d2 = 1.0 / d2;
+                // new = c*cur - kr*ya - wr*yb with (c, ya, yb) = (1, y, 0) for j < q,
+                // (0, -1, 0) for j == q, (1, 0, y) for j > q: no per-element selects
+                double cc[CS], ya[CS], yb[CS];
+#pragma unroll
+                for (int s = 0; s < CS; ++s) {
+                    const int j = lane + 32 * s;
+                    cc[s] = (j == q) ? 0.0 : 1.0;
+                    ya[s] = (j < q) ? y[s] : (j == q ? -1.0 : 0.0);
+                    yb[s] = (j > q) ? y[s] : 0.0;
+                }
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) {
                     const double zr = S.zrow[row0 + r];
                     const double kr = zr * inv_d2;
                     const double wr = (zr + sgd * S.colk[0][row0 + r]) * beta;
 #pragma unroll
-                    for (int s = 0; s < CS; ++s) {
-                        const int j = lane + 32 * s;
-                        const double cur = m[r][s];
-                        m[r][s] = (j < q) ? cur - kr * y[s] : (j == q ? kr : cur - wr * y[s]);
-                    }
+                    for (int s = 0; s < CS; ++s) m[r][s] = fma(-wr, yb[s], fma(-kr, ya[s], cc[s] * m[r][s]));
                 }
 #pragma unroll
                 for (int s = 0; s < CS; ++s) {
