@@ -292,7 +292,7 @@ extern "C" int fsae_condense_host(fsae_ctx* ctx, int model, int B, int N, double
     int NX, NU, NS;
     if (!ctx || model_dims(model, NX, NU, NS) != FSAE_OK || B < 0 || N <= 0 || N > 80 || !x0 || !x_ref || !x_lin || !u_lin)
         return FSAE_ERR_ARG;
-    if (model != FSAE_MODEL_KINEMATIC) { ctx->err = "condense: dynamic model not built yet"; return FSAE_ERR_UNSUPPORTED; }
+    if (model == FSAE_MODEL_DYNAMIC && N > 40) { ctx->err = "condense: dynamic model supports N <= 40"; return FSAE_ERR_UNSUPPORTED; }
     if (B == 0) return FSAE_OK;
     int rc = check_ids(ctx, B, track_id, param_id);
     if (rc) return rc;
@@ -327,7 +327,8 @@ extern "C" int fsae_condense_host(fsae_ctx* ctx, int model, int B, int N, double
     a.ub = (lb && ub) ? (double*)ctx->out[6].p : nullptr;
     a.A_bar = (double*)ctx->out[7].p; a.B_bar = (double*)ctx->out[8].p; a.d_bar = (double*)ctx->out[9].p;
     a.cconst = cost_const ? (double*)ctx->out[10].p : nullptr;
-    condense_kernel<KinModel, 80><<<B, 256, 0, ctx->stream>>>(a);
+    if (model == FSAE_MODEL_KINEMATIC) condense_kernel<KinModel, 80><<<B, 256, 0, ctx->stream>>>(a);
+    else condense_kernel<DynModel, 40><<<B, 256, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     for (int i = 0; i < 11; ++i)
@@ -352,10 +353,10 @@ static int launch_fused_v1(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
     return FSAE_OK;
 }
 
-template <class Model, int N>
+template <class Model, int N, int MINB>
 static int launch_fused_v2(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
     using S_t = SmemV2<Model, N>;
-    auto kern = ltvmpc_fused_v2_kernel<Model, N>;
+    auto kern = ltvmpc_fused_v2_kernel<Model, N, MINB>;
     static bool configured[64] = {false};
     if (!configured[ctx->device & 63]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S_t)));
@@ -393,11 +394,13 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
     int rc = FSAE_ERR_UNSUPPORTED;
     if (model == FSAE_MODEL_KINEMATIC) {
         const bool v1 = ctx->kernel_version == 1;
-        if (N == 40) rc = v1 ? launch_fused_v1<KinModel, 40, 256>(ctx, a, st) : launch_fused_v2<KinModel, 40>(ctx, a, st);
-        else if (N == 20) rc = v1 ? launch_fused_v1<KinModel, 20, 256>(ctx, a, st) : launch_fused_v2<KinModel, 20>(ctx, a, st);
+        if (N == 40) rc = v1 ? launch_fused_v1<KinModel, 40, 256>(ctx, a, st) : launch_fused_v2<KinModel, 40, 2>(ctx, a, st);
+        else if (N == 20) rc = v1 ? launch_fused_v1<KinModel, 20, 256>(ctx, a, st) : launch_fused_v2<KinModel, 20, 2>(ctx, a, st);
         else ctx->err = "kinematic fused step: horizon must be 20 or 40";
     } else {
-        ctx->err = "dynamic fused step not built yet";
+        if (N == 40) rc = launch_fused_v2<DynModel, 40, 1>(ctx, a, st);
+        else if (N == 20) rc = launch_fused_v2<DynModel, 20, 1>(ctx, a, st);
+        else ctx->err = "dynamic fused step: horizon must be 20 or 40";
     }
     if (rc != FSAE_OK) return rc;
     CK(cudaEventRecord(ctx->ev1, st));

@@ -71,6 +71,7 @@ struct SmemV1 {
     double ul[N * D::NU];
     double pc[N * C::NPC];
     double g0[N * C::NG0];
+    double cg[C::NCG];
     double rlo[D::NROWS], rup[D::NROWS];
     double x[D::nV], g[D::nV], y[D::nV], z[D::nV], wv[D::nV], kv[D::nV], nv[D::nV], lam[D::nV];
     double part[3 * D::nV];
@@ -198,11 +199,11 @@ __device__ __forceinline__ double normal_entry(const SmemV1<Model, N, NT>& S, in
     const double* pc = S.pc + k * C::NPC;
     double v = 0.0;
 #pragma unroll
-    for (int c = 0; c < C::NCR; ++c) v += C::row_coef(r, c, pc) * S.Bc[c * D::NPK + D::pk(k, j)];
+    for (int c = 0; c < C::NCR; ++c) v += C::row_coef(r, c, pc, S.cg) * S.Bc[c * D::NPK + D::pk(k, j)];
 #pragma unroll
     for (int c = 0; c < C::NINT; ++c)
-        if (C::int_ucol(c) == uc) v += C::row_coef(r, C::NCR + c, pc) * dt;
-    if (step == k) v += C::row_ucoef(r, uc, pc);
+        if (C::int_ucol(c) == uc) v += C::row_coef(r, C::NCR + c, pc, S.cg) * dt;
+    if (step == k) v += C::row_ucoef(r, uc, pc, S.cg);
     return sg * v;
 }
 
@@ -255,6 +256,8 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
             for (int i = 0; i < NX * NU; ++i) S.B1[i] = Bc_[i] * dt;   // QUIRK: B(:,:,1) everywhere
         }
         C::step_coefs(S.xl + k * NX, S.ul + k * NU, tr, P, S.pc + k * C::NPC, S.g0 + k * C::NG0);
+    } else if (tid == N) {
+        C::problem_consts(P, S.cg);
     }
     __syncthreads();
 
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
         for (int t = tid; t < D::NROWS; t += NT) {
             const int r = t / N, k = t - r * N;
             double lo, up;
-            C::row_bounds(r, S.xf + k * NX, S.xl + k * NX, S.ul + k * NU, S.pc + k * C::NPC, S.g0 + k * C::NG0, P, lo, up);
+            C::row_bounds(r, S.xf + k * NX, S.xl + k * NX, S.ul + k * NU, S.pc + k * C::NPC, S.g0 + k * C::NG0, S.cg, P, lo, up);
             S.rlo[t] = lo;
             S.rup[t] = up;
         }
@@ -522,7 +525,7 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
                 double xsk[C::NXS];
 #pragma unroll
                 for (int c = 0; c < C::NXS; ++c) xsk[c] = S.xs[c * N + k];
-                const double rv = C::row_value(r, xsk, S.pc + k * C::NPC, S.x[NU * k]);
+                const double rv = C::row_value(r, xsk, S.pc + k * C::NPC, S.cg, S.x[NU * k]);
                 const int sl = C::row_slack(r);
                 const double sv = sl >= 0 ? S.x[nU + sl] : 0.0;
                 vlo = rv + sv - S.rlo[rr];

@@ -48,6 +48,7 @@ struct SmemV2 {
     double ul[N * D::NU];
     double pc[N * C::NPC];
     double g0[N * C::NG0];
+    double cg[C::NCG];
     double rlo[D::NROWS], rup[D::NROWS];
     double rn2[D::NROWS];              // squared norm of each row's normal (linear-dependence test)
     double x[G::RP], g[G::RP];
@@ -149,8 +150,8 @@ __device__ __forceinline__ bool rs_is_writer() {
     return RH == 16 ? ((lane & 1) == 0) : ((lane & 3) == 0);
 }
 
-template <class Model, int N>
-__global__ void __launch_bounds__(256, 2) ltvmpc_fused_v2_kernel(BatchArgs a) {
+template <class Model, int N, int MINB>
+__global__ void __launch_bounds__(256, MINB) ltvmpc_fused_v2_kernel(BatchArgs a) {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
     using G = CfgV2<Model, N>;
@@ -197,6 +198,8 @@ __global__ void __launch_bounds__(256, 2) ltvmpc_fused_v2_kernel(BatchArgs a) {
             for (int i = 0; i < NX * NU; ++i) S.B1[i] = Bc_[i] * dt;   // QUIRK: B(:,:,1) everywhere
         }
         C::step_coefs(S.xl + k * NX, S.ul + k * NU, tr, P, S.pc + k * C::NPC, S.g0 + k * C::NG0);
+    } else if (tid == N) {
+        C::problem_consts(P, S.cg);
     }
     __syncthreads();
 
@@ -297,22 +300,26 @@ __global__ void __launch_bounds__(256, 2) ltvmpc_fused_v2_kernel(BatchArgs a) {
         for (int t = tid; t < D::NROWS; t += NT) {
             const int r = t / N, k = t - r * N;
             double lo, up;
-            C::row_bounds(r, S.xf + k * NX, S.xl + k * NX, S.ul + k * NU, S.pc + k * C::NPC, S.g0 + k * C::NG0, P, lo, up);
+            C::row_bounds(r, S.xf + k * NX, S.xl + k * NX, S.ul + k * NU, S.pc + k * C::NPC, S.g0 + k * C::NG0, S.cg, P, lo, up);
             S.rlo[t] = lo;
             S.rup[t] = up;
-            // squared norm of the row normal (u part + slack entry)
+            // squared norm of the row normal (u part + slack entry); only a scale for the
+            // linear-dependence threshold, so large row sets use 1
             const double* pc = S.pc + k * C::NPC;
-            double n2 = (C::row_slack(r) >= 0) ? 1.0 : 0.0;
-            for (int j = 0; j < NU * (k + 1); ++j) {
-                const int step = j / NU, uc = j - step * NU;
-                double v = 0.0;
+            double n2 = 1.0;
+            if (D::NROWS <= 256) {
+                n2 = (C::row_slack(r) >= 0) ? 1.0 : 0.0;
+                for (int j = 0; j < NU * (k + 1); ++j) {
+                    const int step = j / NU, uc = j - step * NU;
+                    double v = 0.0;
 #pragma unroll
-                for (int c = 0; c < C::NCR; ++c) v += C::row_coef(r, c, pc) * S.Bf[C::cons_real(c) * D::NPK + D::pk(k, j)];
+                    for (int c = 0; c < C::NCR; ++c) v += C::row_coef(r, c, pc, S.cg) * S.Bf[C::cons_real(c) * D::NPK + D::pk(k, j)];
 #pragma unroll
-                for (int c = 0; c < C::NINT; ++c)
-                    if (C::int_ucol(c) == uc) v += C::row_coef(r, C::NCR + c, pc) * dt;
-                if (step == k) v += C::row_ucoef(r, uc, pc);
-                n2 += v * v;
+                    for (int c = 0; c < C::NINT; ++c)
+                        if (C::int_ucol(c) == uc) v += C::row_coef(r, C::NCR + c, pc, S.cg) * dt;
+                    if (step == k) v += C::row_ucoef(r, uc, pc, S.cg);
+                    n2 += v * v;
+                }
             }
             S.rn2[t] = n2;
         }
@@ -647,7 +654,7 @@ __global__ void __launch_bounds__(256, 2) ltvmpc_fused_v2_kernel(BatchArgs a) {
                 double xsk[C::NXS];
 #pragma unroll
                 for (int c = 0; c < C::NXS; ++c) xsk[c] = S.xs[c * N + k];
-                const double rv = C::row_value(r, xsk, S.pc + k * C::NPC, S.x[NU * k]);
+                const double rv = C::row_value(r, xsk, S.pc + k * C::NPC, S.cg, S.x[NU * k]);
                 const int sl = C::row_slack(r);
                 const double sv = sl >= 0 ? S.x[nU + sl] : 0.0;
                 vlo = rv + sv - S.rlo[rr];
@@ -716,11 +723,11 @@ __global__ void __launch_bounds__(256, 2) ltvmpc_fused_v2_kernel(BatchArgs a) {
                             double acc = 0.0;
 #pragma unroll
                             for (int c = 0; c < C::NCR; ++c)
-                                acc += C::row_coef(r, c, pc) * S.Bf[C::cons_real(c) * D::NPK + D::pk(k, i)];
+                                acc += C::row_coef(r, c, pc, S.cg) * S.Bf[C::cons_real(c) * D::NPK + D::pk(k, i)];
 #pragma unroll
                             for (int c = 0; c < C::NINT; ++c)
-                                if (C::int_ucol(c) == uc) acc += C::row_coef(r, C::NCR + c, pc) * dt;
-                            if (step == k) acc += C::row_ucoef(r, uc, pc);
+                                if (C::int_ucol(c) == uc) acc += C::row_coef(r, C::NCR + c, pc, S.cg) * dt;
+                            if (step == k) acc += C::row_ucoef(r, uc, pc, S.cg);
                             v = sg * acc;
                         }
                     }

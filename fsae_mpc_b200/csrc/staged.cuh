@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(256) condense_kernel(CondenseArgs a) {
     __shared__ double xf[MAXN * NX];
     __shared__ double pc[MAXN * (C::NPC > 0 ? C::NPC : 1)];
     __shared__ double g0[MAXN * C::NG0];
+    __shared__ double cg[C::NCG];
     __shared__ double red[256];
     const fsae_params& P = a.params[a.param_id ? a.param_id[b] : 0];
     const DevTrack tr = a.tracks[a.track_id ? a.track_id[b] : 0];
@@ -109,6 +110,8 @@ __global__ void __launch_bounds__(256) condense_kernel(CondenseArgs a) {
         if (k == 0)
             for (int i = 0; i < NX * NU; ++i) B1[i] = Bc[i] * dt;
         C::step_coefs(x, u, tr, P, pc + k * C::NPC, g0 + k * C::NG0);
+    } else if (tid == N) {
+        C::problem_consts(P, cg);
     }
     for (int t = tid; t < nXN * nV; t += NT) Bbar[t] = 0.0;
     __syncthreads();
@@ -222,10 +225,10 @@ __global__ void __launch_bounds__(256) condense_kernel(CondenseArgs a) {
             double v = 0.0;
             if (j < nU) {
                 for (int c = 0; c < C::NXS; ++c) {
-                    const double cf = C::row_coef(r, c, pc + k * C::NPC);
+                    const double cf = C::row_coef(r, c, pc + k * C::NPC, cg);
                     if (cf != 0.0) v += cf * Bbar[(size_t)j * nXN + k * NX + C::xs_state(c)];
                 }
-                if (j / NU == k) v += C::row_ucoef(r, j % NU, pc + k * C::NPC);
+                if (j / NU == k) v += C::row_ucoef(r, j % NU, pc + k * C::NPC, cg);
             } else {
                 const int sl = C::row_slack(r);
                 if (sl >= 0 && j == nU + sl) v = C::ref_slack_sign(row, N);
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(256) condense_kernel(CondenseArgs a) {
             int r, k, kind;
             C::ref_decode(row, N, r, k, kind);
             double lo, up;
-            C::row_bounds(r, xf + k * NX, xl + k * NX, ul + k * NU, pc + k * C::NPC, g0 + k * C::NG0, P, lo, up);
+            C::row_bounds(r, xf + k * NX, xl + k * NX, ul + k * NU, pc + k * C::NPC, g0 + k * C::NG0, cg, P, lo, up);
             if (kind == 1) up = P.soft_far;
             else if (kind == 2) lo = -P.soft_far;
             else if (kind == 3) up = INFINITY;
