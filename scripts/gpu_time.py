@@ -3,14 +3,21 @@ sys.path.insert(0, '.')
 import fsae_mpc_b200 as fm
 from fsae_mpc_b200 import workload as wl
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+model = sys.argv[2] if len(sys.argv) > 2 else "kinematic"
+track = sys.argv[3] if len(sys.argv) > 3 else "fsg2019"
 mpc = fm.FsaeMpc(0)
 for tid, (n, t) in enumerate(wl.load_tracks().items()):
     mpc.set_track(tid, t[0], t[1], t[2])
-x0, xr, xl, ul = wl.perturbed_batch("kinematic", "fsg2019", B, 0)
+x0, xr, xl, ul = wl.perturbed_batch(model, track, B, 0)
+tid = np.full(B, list(wl.load_tracks()).index(track), np.int32)
+pid = None
+if model == "dynamic":
+    mpc.set_params(1, fm.default_params(fm.DYNAMIC)); pid = np.ones(B, np.int32)
+step = mpc.ltvmpc_kinetmatic_curvilinear if model == "kinematic" else mpc.ltvmpc_dynamic_curvilinear
 for rep in range(4):
     mpc.counters(reset=True)
     t = time.time()
-    r = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, 0.05, xl, ul)
+    r = step(x0, xr, 0.05, xl, ul, track_id=tid, param_id=pid)
     dt_host = time.time() - t
     ms = mpc.last_kernel_ms
     a, d, rf = mpc.counters()
