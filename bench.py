@@ -246,12 +246,10 @@ def run_ours(args, rank, local_rank, world):
     d2h = sum(t.numel() * t.element_size() for t in h_out.values())
 
     # ---------------- max over ranks ----------------
-    times = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
-    sums = torch.tensor([float(adds), float(drops), float(refreshes), float(n_bad)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    total_ms, e2e_ms = times.tolist()
+    from fsae_mpc_b200.sharding import reduce_metrics
+    (total_ms, e2e_ms), sums_l = reduce_metrics([total_ms, e2e_ms],
+                                                [adds, drops, refreshes, n_bad], dist, device=dev)
+    sums = torch.tensor(sums_l, dtype=torch.float64)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
