@@ -51,7 +51,8 @@ struct SmemV2 {
     double cg[C::NCG];
     double rlo[D::NROWS], rup[D::NROWS];
     double rn2[D::NROWS];              // squared norm of each row's normal (linear-dependence test)
-    double x[G::RP], g[G::RP];
+    alignas(16) double x[G::RP];
+    double g[G::RP];
     double ypart[2][G::NW][G::CP];     // cross-warp partial sums of M'v (double-buffered)
     double colk[2][G::RP];             // column broadcast (factorisation / column q / drop column)
     double rowv[G::RP];                // per-warp row vector scratch (gradient / H k)
@@ -59,7 +60,6 @@ struct SmemV2 {
     double zrow[G::RP];                // per-warp reduced z
     double wpart[3][G::RP];            // symv partials
     double dvec[G::RP];                // LDL' pivots
-    double xs[C::NXS * N];
     double dd[N * D::NX];
     double red_val[2][G::NW];
     double scal[8];                    // 0 cost const
@@ -591,6 +591,7 @@ __global__ void __launch_bounds__(256, MINB) ltvmpc_fused_v2_kernel(BatchArgs a)
             if (i < nU) S.x[i] = -S.zrow[i];
         }
     }
+    __syncthreads();                           // x complete
 
     // ---------------------------------------------------------------- Goldfarb-Idnani, K-form
     const double tol = P.feas_tol;
@@ -598,70 +599,67 @@ __global__ void __launch_bounds__(256, MINB) ltvmpc_fused_v2_kernel(BatchArgs a)
     int iters = 0, exitflag = FSAE_EXIT_SOLVED, n_add = 0, n_drop = 0, n_refresh = 0;
     int rbuf = 0;
     while (true) {
-        __syncthreads();                       // x complete
-        // P1a: constraint-state perturbations xs
-        {
-            // real constraint rows: 4 lanes per (c, k) row
-            constexpr int NRR = C::NCR * N;
-            for (int base = 0; base < NRR; base += NT / 4) {
-                const int rid = base + (tid >> 2), part = tid & 3;
-                double acc = 0.0;
-                if (rid < NRR) {
-                    const int c = rid / N, k = rid - c * N;
-                    const double* row = S.Bf + C::cons_real(c) * D::NPK + D::pk(k, 0);
-                    const int len = NU * (k + 1);
-                    const int ch = (len + 3) >> 2;
-                    const int j0 = part * ch, j1 = (j0 + ch < len) ? j0 + ch : len;
-                    for (int j = j0; j < j1; ++j) acc += row[j] * S.x[j];
-                }
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                if (rid < NRR && part == 0) S.xs[rid] = acc;
-            }
-            // integrator states: prefix sums, one warp each (warps NW-1, NW-2, ...)
-            if (warp >= NW - C::NINT) {
-                const int ci = NW - 1 - warp;
-                const int uc = C::int_ucol(ci);
-                static_assert(N <= 64, "prefix scan assumes at most 2 steps per lane");
-                const int k0 = 2 * lane, k1 = 2 * lane + 1;
-                const double a0 = (k0 < N) ? S.x[NU * k0 + uc] : 0.0;
-                const double a1 = (k1 < N) ? S.x[NU * k1 + uc] : 0.0;
-                double sc = a0 + a1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double up = __shfl_up_sync(0xffffffffu, sc, o);
-                    if (lane >= o) sc += up;
-                }
-                if (k1 < N) S.xs[(C::NCR + ci) * N + k1] = sc * dt;
-                if (k0 < N) S.xs[(C::NCR + ci) * N + k0] = (sc - a1) * dt;
-            }
-        }
-        __syncthreads();
-        // P1b: most violated inactive constraint side
+        // P1: most violated inactive constraint side.  Threads [0, 4N): 4 lanes per horizon
+        // step k compute the constraint-state perturbations xs[., k] = (B_bar_c x)[., k]
+        // (packed rows, plus the exact prefix sums of the integrator states) and then split
+        // that step's rows among themselves; threads [4N, 4N+nV): the variable bounds.
+        // No shared-memory round trip and no barrier between evaluation and search.
+        static_assert(4 * N + nV <= NT, "P1 thread map needs 4N + nV <= 256");
+        static_assert(NU == 2, "paired (double2) row loads assume two controls per step");
         double best = 0.0;
         int best_i = 0x7fffffff;
-        for (int slot = tid; slot < D::NSLOT; slot += NT) {
-            if (S.status[slot] != 0) continue;
-            double vlo, vup;
-            if (slot < nV) {
+        if (warp < (4 * N + 31) / 32) {
+            const int k = tid >> 2, part = tid & 3;
+            const bool valid = k < N;
+            double acc[C::NXS];
+#pragma unroll
+            for (int c = 0; c < C::NXS; ++c) acc[c] = 0.0;
+            if (valid) {
+                const int len = NU * (k + 1);
+                const int ch = (((len + 3) >> 2) + 1) & ~1;          // even chunk -> 16-byte aligned pairs
+                const int j0 = part * ch, j1 = (j0 + ch < len) ? j0 + ch : len;
+                for (int j = j0; j < j1; j += 2) {
+                    const double2 xx = *reinterpret_cast<const double2*>(&S.x[j]);
+#pragma unroll
+                    for (int c = 0; c < C::NCR; ++c) {
+                        const double2 bb = *reinterpret_cast<const double2*>(&S.Bf[C::cons_real(c) * D::NPK + D::pk(k, j)]);
+                        acc[c] = fma(bb.x, xx.x, fma(bb.y, xx.y, acc[c]));
+                    }
+#pragma unroll
+                    for (int ci = 0; ci < C::NINT; ++ci) acc[C::NCR + ci] += (C::int_ucol(ci) == 0) ? xx.x : xx.y;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C::NXS; ++c) {
+                acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+                acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+            }
+            if (valid) {
+#pragma unroll
+                for (int ci = 0; ci < C::NINT; ++ci) acc[C::NCR + ci] *= dt;
+                const double ua = S.x[NU * k];
+                for (int r = part; r < C::NR; r += 4) {
+                    const int rr = r * N + k, slot = nV + rr;
+                    if (S.status[slot] != 0) continue;
+                    const double rv = C::row_value(r, acc, S.pc + k * C::NPC, S.cg, ua);
+                    const int sl = C::row_slack(r);
+                    const double sv = sl >= 0 ? S.x[nU + sl] : 0.0;
+                    const double vlo = rv + sv - S.rlo[rr];
+                    const double vup = S.rup[rr] - rv + sv;
+                    if (vlo < best) { best = vlo; best_i = slot * 2; }
+                    if (vup < best) { best = vup; best_i = slot * 2 + 1; }
+                }
+            }
+        } else {
+            const int slot = tid - 4 * N;
+            if (slot >= 0 && slot < nV && S.status[slot] == 0) {
                 const double xv = S.x[slot];
                 const double lb = (slot < nU) ? P.u_lb[slot % NU] : 0.0;
                 const double ub = (slot < nU) ? P.u_ub[slot % NU] : INFINITY;
-                vlo = xv - lb;
-                vup = ub - xv;
-            } else {
-                const int rr = slot - nV, r = rr / N, k = rr - r * N;
-                double xsk[C::NXS];
-#pragma unroll
-                for (int c = 0; c < C::NXS; ++c) xsk[c] = S.xs[c * N + k];
-                const double rv = C::row_value(r, xsk, S.pc + k * C::NPC, S.cg, S.x[NU * k]);
-                const int sl = C::row_slack(r);
-                const double sv = sl >= 0 ? S.x[nU + sl] : 0.0;
-                vlo = rv + sv - S.rlo[rr];
-                vup = S.rup[rr] - rv + sv;
+                const double vlo = xv - lb, vup = ub - xv;
+                if (vlo < best) { best = vlo; best_i = slot * 2; }
+                if (vup < best) { best = vup; best_i = slot * 2 + 1; }
             }
-            if (vlo < best) { best = vlo; best_i = slot * 2; }
-            if (vup < best) { best = vup; best_i = slot * 2 + 1; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -698,6 +696,7 @@ __global__ void __launch_bounds__(256, MINB) ltvmpc_fused_v2_kernel(BatchArgs a)
                 const int j = lane + 32 * s;
                 if (j < q) lam[s] = fmax(y[s], 0.0);
             }
+            __syncthreads();                   // x complete
             continue;
         }
         const int pslot = pcode >> 1, pside = (pcode & 1) ? +1 : -1;
@@ -780,6 +779,16 @@ __global__ void __launch_bounds__(256, MINB) ltvmpc_fused_v2_kernel(BatchArgs a)
                 }
                 sp += t * d2;
             }
+            if (full) {
+                // bookkeeping of the add happens BEFORE the barrier that publishes x, so the
+                // next search (which follows the register-only update below without another
+                // barrier) sees a consistent x / status
+                if (tid == 0) {
+                    S.act[q] = pslot * 2 + (pside > 0 ? 1 : 0);
+                    S.status[pslot] = (int8_t)pside;
+                }
+                __syncthreads();               // x complete
+            }
 #pragma unroll
             for (int s = 0; s < CS; ++s) {
                 const int j = lane + 32 * s;
@@ -825,10 +834,6 @@ __global__ void __launch_bounds__(256, MINB) ltvmpc_fused_v2_kernel(BatchArgs a)
                 for (int s = 0; s < CS; ++s) {
                     const int j = lane + 32 * s;
                     if (j == q) lam[s] = lam_p;
-                }
-                if (tid == 0) {
-                    S.act[q] = pslot * 2 + (pside > 0 ? 1 : 0);
-                    S.status[pslot] = (int8_t)pside;
                 }
                 ++q;
                 ++n_add;
