@@ -353,16 +353,16 @@ static int launch_fused_v1(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
     return FSAE_OK;
 }
 
-template <class Model, int N, int MINB>
+template <class Model, int N, int MINB, int NW = 8>
 static int launch_fused_v2(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
-    using S_t = SmemV2<Model, N>;
-    auto kern = ltvmpc_fused_v2_kernel<Model, N, MINB>;
+    using S_t = SmemV2<Model, N, NW>;
+    auto kern = ltvmpc_fused_v2_kernel<Model, N, MINB, NW>;
     static bool configured[64] = {false};
     if (!configured[ctx->device & 63]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S_t)));
         configured[ctx->device & 63] = true;
     }
-    kern<<<a.B, 256, sizeof(S_t), st>>>(a);
+    kern<<<a.B, 32 * NW, sizeof(S_t), st>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return FSAE_OK;

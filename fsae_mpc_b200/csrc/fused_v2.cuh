@@ -21,10 +21,10 @@
 
 namespace fsae {
 
-template <class Model, int N>
+template <class Model, int N, int NW_ = 8>
 struct CfgV2 {
     using D = Dims<Model, N>;
-    static constexpr int NT = 256, NW = 8;
+    static constexpr int NW = NW_, NT = 32 * NW_;
     static constexpr int RPW = (D::nV + NW - 1) / NW;     // rows per warp
     static constexpr int RP = RPW * NW;                     // padded rows
     static constexpr int CS = (D::nV + 31) / 32;            // column slots per lane
@@ -34,11 +34,11 @@ struct CfgV2 {
     static_assert(D::nV < CP, "need one spare padded column for the piggy-backed scalar");
 };
 
-template <class Model, int N>
+template <class Model, int N, int NW_ = 8>
 struct SmemV2 {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
-    using G = CfgV2<Model, N>;
+    using G = CfgV2<Model, N, NW_>;
     double Bf[C::NREAL * D::NPK];      // packed B_bar rows of the "real" states (kept to the end)
     double Hp[D::HP];                  // packed lower triangle of H (drops, refresh, fval)
     double Ad[N * C::NREAL * D::NX];
@@ -150,12 +150,12 @@ __device__ __forceinline__ bool rs_is_writer() {
     return RH == 16 ? ((lane & 1) == 0) : ((lane & 3) == 0);
 }
 
-template <class Model, int N, int MINB>
-__global__ void __launch_bounds__(256, MINB) ltvmpc_fused_v2_kernel(BatchArgs a) {
+template <class Model, int N, int MINB, int NW_ = 8>
+__global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchArgs a) {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
-    using G = CfgV2<Model, N>;
-    using S_t = SmemV2<Model, N>;
+    using G = CfgV2<Model, N, NW_>;
+    using S_t = SmemV2<Model, N, NW_>;
     constexpr int NX = D::NX, NU = D::NU, NS = D::NS, nU = D::nU, nV = D::nV;
     constexpr int NT = G::NT, NW = G::NW, RPW = G::RPW, CS = G::CS, CP = G::CP, RP = G::RP, RH = G::RH;
     extern __shared__ __align__(16) unsigned char smem_raw[];

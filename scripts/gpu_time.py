@@ -14,6 +14,8 @@ pid = None
 if model == "dynamic":
     mpc.set_params(1, fm.default_params(fm.DYNAMIC)); pid = np.ones(B, np.int32)
 step = mpc.ltvmpc_kinetmatic_curvilinear if model == "kinematic" else mpc.ltvmpc_dynamic_curvilinear
+import os
+if os.environ.get("FSAE_KV"): mpc.set_kernel_version(int(os.environ["FSAE_KV"]))
 for rep in range(4):
     mpc.counters(reset=True)
     t = time.time()
