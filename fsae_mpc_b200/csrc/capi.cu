@@ -36,7 +36,8 @@ struct DevBuf {
 
 struct fsae_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
     std::string err;
@@ -109,7 +110,10 @@ extern "C" int fsae_create(fsae_ctx** out, int device) {
     };
     if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice");
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) return fail("stream2");
     if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) return fail("event");
+    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail("event2");
     if (cudaMalloc(&ctx->d_params, sizeof(fsae_params) * FSAE_MAX_PARAM_SETS) != cudaSuccess) return fail("malloc params");
     if (cudaMalloc(&ctx->d_tracks, sizeof(DevTrack) * FSAE_MAX_TRACKS) != cudaSuccess) return fail("malloc tracks");
     if (cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) return fail("malloc counters");
@@ -133,6 +137,10 @@ extern "C" int fsae_destroy(fsae_ctx* ctx) {
     cudaFree(ctx->d_params);
     cudaFree(ctx->d_tracks);
     cudaFree(ctx->d_counters);
+    cudaStreamSynchronize(ctx->stream2);
+    cudaStreamDestroy(ctx->stream2);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -425,30 +433,50 @@ extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double d
     CK(cudaSetDevice(ctx->device));
     const int nU = NU * N, nV = nU + NS, nXN = NX * N;
     const int nC = (model == FSAE_MODEL_KINEMATIC) ? 6 * N : 20 * N;
-    const size_t sz_in[4] = {(size_t)B * NX * 8, (size_t)B * nXN * 8, (size_t)B * nXN * 8, (size_t)B * nU * 8};
-    const double* src[4] = {x0, x_ref, x_lin, u_lin};
-    for (int i = 0; i < 4; ++i) {
-        CK(ctx->in[i].reserve(sz_in[i]));
-        CK(cudaMemcpyAsync(ctx->in[i].p, src[i], sz_in[i], cudaMemcpyHostToDevice, ctx->stream));
-    }
+    // Pipelined in chunks over two streams: the H2D copy of chunk c+1 and the D2H copy of
+    // chunk c-1 overlap the kernel of chunk c (pinned host buffers make the copies truly
+    // asynchronous; pageable ones still work, staged by the driver).
+    const size_t per_in[4] = {(size_t)NX * 8, (size_t)nXN * 8, (size_t)nXN * 8, (size_t)nU * 8};
+    const char* src[4] = {(const char*)x0, (const char*)x_ref, (const char*)x_lin, (const char*)u_lin};
+    for (int i = 0; i < 4; ++i) CK(ctx->in[i].reserve(per_in[i] * B));
     const int32_t *d_tid, *d_pid;
     rc = upload_ids(ctx, B, track_id, param_id, &d_tid, &d_pid);
     if (rc) return rc;
-    const size_t sz_out[8] = {(size_t)B * nU * 8, (size_t)B * nXN * 8, (size_t)B * 4, (size_t)B * 8,
-                              (size_t)B * NS * 8, (size_t)B * 4, (size_t)B * nV, (size_t)B * nC};
-    void* dst[8] = {u_opt, x_opt, exitflag, fval, slack_opt, iters, workingSetB, workingSetC};
-    for (int i = 0; i < 8; ++i) CK(ctx->out[i].reserve(sz_out[i]));
-    rc = fsae_ltvmpc_dev(ctx, model, B, N, dt, d_tid, d_pid,
-                         (const double*)ctx->in[0].p, (const double*)ctx->in[1].p,
-                         (const double*)ctx->in[2].p, (const double*)ctx->in[3].p,
-                         (double*)ctx->out[0].p, (double*)ctx->out[1].p, (int32_t*)ctx->out[2].p,
-                         (double*)ctx->out[3].p, (double*)ctx->out[4].p,
-                         iters ? (int32_t*)ctx->out[5].p : nullptr,
-                         workingSetB ? (int8_t*)ctx->out[6].p : nullptr,
-                         workingSetC ? (int8_t*)ctx->out[7].p : nullptr, ctx->stream);
-    if (rc) return rc;
-    for (int i = 0; i < 8; ++i)
-        if (dst[i]) CK(cudaMemcpyAsync(dst[i], ctx->out[i].p, sz_out[i], cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t per_out[8] = {(size_t)nU * 8, (size_t)nXN * 8, 4, 8, (size_t)NS * 8, 4, (size_t)nV, (size_t)nC};
+    char* dst[8] = {(char*)u_opt, (char*)x_opt, (char*)exitflag, (char*)fval, (char*)slack_opt, (char*)iters,
+                    (char*)workingSetB, (char*)workingSetC};
+    for (int i = 0; i < 8; ++i) CK(ctx->out[i].reserve(per_out[i] * B));
+    const int nchunk = (B >= 16384) ? 8 : 1;
+    const int per = (B + nchunk - 1) / nchunk;
+    if (nchunk > 1) {
+        // stream2 starts after whatever is already queued on the main stream (ids upload)
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    }
+    for (int c = 0; c < nchunk; ++c) {
+        const int lo = c * per, n = (lo + per <= B) ? per : B - lo;
+        if (n <= 0) break;
+        cudaStream_t st = (c & 1) ? ctx->stream2 : ctx->stream;
+        for (int i = 0; i < 4; ++i)
+            CK(cudaMemcpyAsync((char*)ctx->in[i].p + per_in[i] * lo, src[i] + per_in[i] * lo, per_in[i] * n,
+                               cudaMemcpyHostToDevice, st));
+        auto o = [&](int i) { return (char*)ctx->out[i].p + per_out[i] * lo; };
+        rc = fsae_ltvmpc_dev(ctx, model, n, N, dt, d_tid ? d_tid + lo : nullptr, d_pid ? d_pid + lo : nullptr,
+                             (const double*)((char*)ctx->in[0].p + per_in[0] * lo),
+                             (const double*)((char*)ctx->in[1].p + per_in[1] * lo),
+                             (const double*)((char*)ctx->in[2].p + per_in[2] * lo),
+                             (const double*)((char*)ctx->in[3].p + per_in[3] * lo),
+                             (double*)o(0), (double*)o(1), (int32_t*)o(2), (double*)o(3), (double*)o(4),
+                             iters ? (int32_t*)o(5) : nullptr, workingSetB ? (int8_t*)o(6) : nullptr,
+                             workingSetC ? (int8_t*)o(7) : nullptr, st);
+        if (rc) return rc;
+        for (int i = 0; i < 8; ++i)
+            if (dst[i]) CK(cudaMemcpyAsync(dst[i] + per_out[i] * lo, o(i), per_out[i] * n, cudaMemcpyDeviceToHost, st));
+    }
+    if (nchunk > 1) {
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return FSAE_OK;
 }
