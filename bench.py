@@ -148,6 +148,7 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("FSAE_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -300,7 +301,8 @@ def run_ours(args, rank, local_rank, world):
             "solver": {"exitflag_nonzero": int(sums[3].item()), "iters_mean": iters_mean,
                        "adds_per_qp": sums[0].item() / n_qp, "drops_per_qp": sums[1].item() / n_qp,
                        "refreshes_per_qp": sums[2].item() / n_qp}}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

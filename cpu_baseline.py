@@ -42,8 +42,14 @@ class Baseline:
         self.xs = np.asfortranarray(track[0], dtype=np.float64)
         self.ys = np.asfortranarray(track[1], dtype=np.float64)
         self.dl = float(track[2])
+        # all host cores the process may use, explicitly: torchrun exports OMP_NUM_THREADS=1
+        if not threads:
+            try:
+                threads = len(os.sched_getaffinity(0))
+            except AttributeError:
+                threads = os.cpu_count() or 1
         self.threads = threads
-        self.cores = threads or (os.cpu_count() or 1)
+        self.cores = threads
         self.last = None
 
     def run(self, x0, x_ref, x_lin, u_lin, dt):
