@@ -202,6 +202,48 @@ class FsaeMpc:
         """mpc/ltv/dynamic/ltvmpc_dynamic_curvilinear.m:1."""
         return self._ltvmpc(DYNAMIC, x0, x_ref, dt, x_lin, u_lin, track_id, param_id)
 
+    def qpOASES(self, H, g, A, lb, ub, lbA, ubA):
+        """[x,fval,exitflag,iter,lambda,auxOutput] = qpOASES(H,g,A,lb,ub,lbA,ubA)
+        (optimizers/matlab/qpOASES/qpOASES.m:22) for B dense QPs of one shape.
+        H (B,nV,nV) symmetric, g (B,nV), A (B,nC,nV), bounds (B,nV)/(B,nC).  Returns a dict."""
+        H = np.ascontiguousarray(H, dtype=np.float64)
+        B, nV = H.shape[0], H.shape[1]
+        A = np.zeros((B, 0, nV)) if A is None else np.asarray(A, dtype=np.float64)
+        nC = A.shape[1]
+        At = np.ascontiguousarray(A.transpose(0, 2, 1))          # column-major [nC x nV] per problem
+        g, lb, ub = (_f64(v, (B, nV)) for v in (g, lb, ub))
+        lbA = _f64(lbA if nC else np.zeros((B, 0)), (B, nC))
+        ubA = _f64(ubA if nC else np.zeros((B, 0)), (B, nC))
+        o = dict(x=np.empty((B, nV)), fval=np.empty(B), exitflag=np.empty(B, np.int32), iter=np.empty(B, np.int32),
+                 lam=np.empty((B, nV + nC)), workingSetB=np.empty((B, nV), np.int8),
+                 workingSetC=np.empty((B, max(nC, 1)), np.int8))
+        bp = lambda a: a.ctypes.data_as(C.POINTER(C.c_int8))
+        self._check(self._lib.fsae_qpoases_host(
+            self._ctx, B, nV, nC, _dp(H), _dp(g), _dp(At), _dp(lb), _dp(ub), _dp(lbA), _dp(ubA),
+            _dp(o["x"]), _dp(o["fval"]), _ip(o["exitflag"]), _ip(o["iter"]), _dp(o["lam"]),
+            bp(o["workingSetB"]), bp(o["workingSetC"])), "fsae_qpoases_host")
+        o["workingSetC"] = o["workingSetC"][:, :nC]
+        return o
+
+    def ltvmpc_sqp(self, model, x0, x_ref, dt, x_lin, u_lin, n_sqp, track_id=None, param_id=None):
+        """n_sqp repeated relinearise + QP passes on a frozen (x0, x_ref): fsae_ltvmpc_sqp_host."""
+        NX, NU, NS = _DIMS[model]
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        B = x0.shape[0]
+        N = np.asarray(x_ref).shape[1]
+        x0 = _f64(x0, (B, NX))
+        x_ref = _f64(x_ref, (B, N, NX))
+        x_lin = _f64(x_lin, (B, N, NX))
+        u_lin = _f64(u_lin, (B, N, NU))
+        t, p = self._ids(B, track_id, param_id)
+        r = MpcResult(np.empty((B, NU * N)), np.empty((B, NX * N)), np.empty(B, np.int32), np.empty(B),
+                      np.empty((B, NS)), np.empty(B, np.int32), np.zeros((B, 0), np.int8), np.zeros((B, 0), np.int8))
+        self._check(self._lib.fsae_ltvmpc_sqp_host(
+            self._ctx, model, B, N, float(dt), int(n_sqp), _ip(t), _ip(p), _dp(x0), _dp(x_ref), _dp(x_lin), _dp(u_lin),
+            _dp(r.u_opt), _dp(r.x_opt), _ip(r.exitflag), _dp(r.fval), _dp(r.slack_opt), _ip(r.iters)),
+            "fsae_ltvmpc_sqp_host")
+        return r
+
     def ltvmpc_dev(self, model, B, N, dt, ptrs, stream=0):
         """Device-pointer entry (fsae_ltvmpc_dev).  `ptrs` is a dict of integer device
         addresses: x0,x_ref,x_lin,u_lin,u_opt,x_opt,exitflag,fval,slack_opt and optionally

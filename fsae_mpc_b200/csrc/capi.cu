@@ -12,6 +12,7 @@
 #include "fused_v2.cuh"
 #include "staged.cuh"
 #include "probe.cuh"
+#include "dense_qp.cuh"
 
 using namespace fsae;
 
@@ -481,14 +482,118 @@ extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double d
     return FSAE_OK;
 }
 
+// merge exit flags / iteration counts across SQP passes
+__global__ void sqp_merge_kernel(int B, const int32_t* ef_pass, const int32_t* it_pass, int32_t* ef_acc, int32_t* it_acc, int first) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    if (first) { ef_acc[i] = ef_pass[i]; it_acc[i] = it_pass[i]; }
+    else { if (ef_acc[i] == 0) ef_acc[i] = ef_pass[i]; it_acc[i] += it_pass[i]; }
+}
+
+extern "C" int fsae_ltvmpc_sqp_host(fsae_ctx* ctx, int model, int B, int N, double dt, int n_sqp,
+                                    const int32_t* track_id, const int32_t* param_id,
+                                    const double* x0, const double* x_ref,
+                                    const double* x_lin, const double* u_lin,
+                                    double* u_opt, double* x_opt, int32_t* exitflag, double* fval,
+                                    double* slack_opt, int32_t* iters) {
+    int NX, NU, NS;
+    if (!ctx || model_dims(model, NX, NU, NS) != FSAE_OK || B < 0 || n_sqp < 1 || !x0 || !x_ref || !x_lin || !u_lin ||
+        !u_opt || !x_opt || !exitflag || !fval || !slack_opt)
+        return FSAE_ERR_ARG;
+    if (B == 0) return FSAE_OK;
+    int rc = check_ids(ctx, B, track_id, param_id);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int nU = NU * N, nXN = NX * N;
+    const size_t sz_in[4] = {(size_t)B * NX * 8, (size_t)B * nXN * 8, (size_t)B * nXN * 8, (size_t)B * nU * 8};
+    const double* src[4] = {x0, x_ref, x_lin, u_lin};
+    for (int i = 0; i < 4; ++i) {
+        CK(ctx->in[i].reserve(sz_in[i]));
+        CK(cudaMemcpyAsync(ctx->in[i].p, src[i], sz_in[i], cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int32_t *d_tid, *d_pid;
+    rc = upload_ids(ctx, B, track_id, param_id, &d_tid, &d_pid);
+    if (rc) return rc;
+    // out[0]/out[1] double as the next pass's u_lin/x_lin (x_opt's stacked layout IS the
+    // [N_x x N] column-major layout of x_lin); ping-pong with out[8]/out[9]
+    const size_t sz_out[6] = {(size_t)B * nU * 8, (size_t)B * nXN * 8, (size_t)B * 4, (size_t)B * 8, (size_t)B * NS * 8, (size_t)B * 4};
+    for (int i = 0; i < 6; ++i) CK(ctx->out[i].reserve(sz_out[i]));
+    CK(ctx->out[8].reserve(sz_out[0]));
+    CK(ctx->out[9].reserve(sz_out[1]));
+    CK(ctx->out[10].reserve(sz_out[2]));
+    CK(ctx->out[11].reserve(sz_out[5]));
+    const double* xl = (const double*)ctx->in[2].p;
+    const double* ul = (const double*)ctx->in[3].p;
+    double *uo = nullptr, *xo = nullptr;
+    for (int it = 0; it < n_sqp; ++it) {
+        uo = (double*)((it & 1) ? ctx->out[8].p : ctx->out[0].p);
+        xo = (double*)((it & 1) ? ctx->out[9].p : ctx->out[1].p);
+        rc = fsae_ltvmpc_dev(ctx, model, B, N, dt, d_tid, d_pid, (const double*)ctx->in[0].p, (const double*)ctx->in[1].p,
+                             xl, ul, uo, xo, (int32_t*)ctx->out[10].p, (double*)ctx->out[3].p, (double*)ctx->out[4].p,
+                             (int32_t*)ctx->out[11].p, nullptr, nullptr, ctx->stream);
+        if (rc) return rc;
+        sqp_merge_kernel<<<(B + 255) / 256, 256, 0, ctx->stream>>>(B, (const int32_t*)ctx->out[10].p, (const int32_t*)ctx->out[11].p,
+                                                                  (int32_t*)ctx->out[2].p, (int32_t*)ctx->out[5].p, it == 0);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        xl = xo;
+        ul = uo;
+    }
+    CK(cudaMemcpyAsync(u_opt, uo, sz_out[0], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(x_opt, xo, sz_out[1], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(exitflag, ctx->out[2].p, sz_out[2], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(fval, ctx->out[3].p, sz_out[3], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(slack_opt, ctx->out[4].p, sz_out[4], cudaMemcpyDeviceToHost, ctx->stream));
+    if (iters) CK(cudaMemcpyAsync(iters, ctx->out[5].p, sz_out[5], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSAE_OK;
+}
+
 extern "C" int fsae_qpoases_host(fsae_ctx* ctx, int B, int nV, int nC,
                                  const double* H, const double* g, const double* A,
                                  const double* lb, const double* ub, const double* lbA, const double* ubA,
                                  double* x, double* fval, int32_t* exitflag, int32_t* iters,
                                  double* lambda, int8_t* workingSetB, int8_t* workingSetC) {
-    if (!ctx) return FSAE_ERR_ARG;
-    ctx->err = "dense qpOASES drop-in not built yet";
-    return FSAE_ERR_UNSUPPORTED;
+    constexpr int NVMAX = 95;
+    if (!ctx || B < 0 || nV <= 0 || nC < 0 || !H || !g || !lb || !ub || !x || !fval || !exitflag ||
+        (nC > 0 && (!A || !lbA || !ubA)))
+        return FSAE_ERR_ARG;
+    if (nV > NVMAX) { ctx->err = "fsae_qpoases_host: nV > 95 is not supported by this build"; return FSAE_ERR_UNSUPPORTED; }
+    if (B == 0) return FSAE_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t szi[7] = {(size_t)B * nV * nV * 8, (size_t)B * nV * 8, (size_t)B * nC * nV * 8, (size_t)B * nV * 8,
+                           (size_t)B * nV * 8, (size_t)B * nC * 8, (size_t)B * nC * 8};
+    const double* src[7] = {H, g, A, lb, ub, lbA, ubA};
+    for (int i = 0; i < 7; ++i) {
+        CK(ctx->in[i].reserve(szi[i] ? szi[i] : 8));
+        if (szi[i]) CK(cudaMemcpyAsync(ctx->in[i].p, src[i], szi[i], cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const size_t szo[7] = {(size_t)B * nV * 8, (size_t)B * 8, (size_t)B * 4, (size_t)B * 4, (size_t)B * (nV + nC) * 8,
+                           (size_t)B * nV, (size_t)B * (nC ? nC : 1)};
+    void* dst[7] = {x, fval, exitflag, iters, lambda, workingSetB, workingSetC};
+    for (int i = 0; i < 7; ++i) CK(ctx->out[i].reserve(szo[i]));
+    DenseArgs a;
+    a.B = B; a.nV = nV; a.nC = nC;
+    a.H = (const double*)ctx->in[0].p; a.g = (const double*)ctx->in[1].p; a.A = (const double*)ctx->in[2].p;
+    a.lb = (const double*)ctx->in[3].p; a.ub = (const double*)ctx->in[4].p;
+    a.lbA = (const double*)ctx->in[5].p; a.ubA = (const double*)ctx->in[6].p;
+    a.x = (double*)ctx->out[0].p; a.fval = (double*)ctx->out[1].p; a.exitflag = (int32_t*)ctx->out[2].p;
+    a.iters = iters ? (int32_t*)ctx->out[3].p : nullptr;
+    a.lambda = lambda ? (double*)ctx->out[4].p : nullptr;
+    a.wsB = workingSetB ? (int8_t*)ctx->out[5].p : nullptr;
+    a.wsC = (workingSetC && nC) ? (int8_t*)ctx->out[6].p : nullptr;
+    a.feas_tol = ctx->h_params[0].feas_tol; a.flat_eps = ctx->h_params[0].flat_eps; a.max_iter = ctx->h_params[0].max_iter;
+    a.counters = ctx->d_counters;
+    const size_t smem = sizeof(DenseSm<NVMAX>) + (size_t)nV + nC + 16;
+    auto kern = dense_qp_kernel<NVMAX>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, 256, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    for (int i = 0; i < 7; ++i)
+        if (dst[i] && (i != 6 || nC)) CK(cudaMemcpyAsync(dst[i], ctx->out[i].p, szo[i], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSAE_OK;
 }
 
 // debug / test taps -------------------------------------------------------------------

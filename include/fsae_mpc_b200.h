@@ -156,6 +156,19 @@ int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N_steps, double dt,
                     double* slack_opt, int32_t* iters,
                     int8_t* workingSetB, int8_t* workingSetC, void* stream);
 
+/* ---- sequential QP: n_sqp repeated relinearise + condense + QP passes per problem, each
+ * pass linearising at the previous pass's (x_opt, u_opt) -- BASELINE.json configs[3]
+ * ("mpc/nonlinear SQP: repeated relinearise+QP iterations per step").  It is exactly what
+ * main.m:113-118 does across consecutive time steps (x_lin/u_lin = previous x_opt/u_opt),
+ * iterated on a frozen x0/x_ref.  n_sqp = 1 is fsae_ltvmpc_host.  Outputs are those of the
+ * last pass; exitflag is the first non-zero flag met (0 if every pass solved). */
+int fsae_ltvmpc_sqp_host(fsae_ctx* ctx, int model, int B, int N_steps, double dt, int n_sqp,
+                         const int32_t* track_id, const int32_t* param_id,
+                         const double* x0, const double* x_ref,
+                         const double* x_lin, const double* u_lin,
+                         double* u_opt, double* x_opt, int32_t* exitflag, double* fval,
+                         double* slack_opt, int32_t* iters);
+
 /* ---- [x,fval,exitflag,iter,lambda,auxOutput] = qpOASES(H,g,A,lb,ub,lbA,ubA) ----------
  * (optimizers/matlab/qpOASES/qpOASES.m:22) for B independent dense QPs of one shape.
  * H [nV x nV x B] symmetric, A [nC x nV x B] column-major.  lambda [ (nV+nC) x B ] in

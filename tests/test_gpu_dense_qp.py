@@ -1,0 +1,72 @@
+"""GPU: the dense qpOASES drop-in (fsae_qpoases_host) against the oracle QP solver -- on the
+condensed MPC QPs exactly as the reference hands them to qpOASES (reference-executed H, f, xA,
+lb, ub, lbA, ubA) and on random QPs with bounds, two-sided rows and infeasible cases."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_dense_qp_on_reference_condensed_kinematic(mpc):
+    from oracle import qp
+    g = load_golden("reference_m_kinematic_fsg2019.npz")
+    o = mpc.qpOASES(g["H"], g["f"], g["xA"], g["lb"], g["ub"], g["lbA"], g["ubA"])
+    assert (o["exitflag"] == 0).all()
+    nU = g["u_opt"].shape[1]
+    scale = np.maximum(1.0, np.abs(g["u_opt"]).max(axis=1))
+    assert (np.abs(o["x"][:, :nU] - g["u_opt"]).max(axis=1) / scale).max() < 1e-6
+    assert np.abs(o["x"][:, nU:] - g["slack"]).max() < 1e-7
+    for b in range(g["H"].shape[0]):
+        sol = qp.qpoases(g["H"][b], g["f"][b], g["xA"][b], g["lb"][b], g["ub"][b], g["lbA"][b], g["ubA"][b])
+        assert abs(o["fval"][b] - sol.fval) < 1e-7 * (1 + abs(sol.fval))
+        assert np.array_equal(o["workingSetB"][b], sol.workingSetB)
+        assert np.array_equal(o["workingSetC"][b], sol.workingSetC)
+        k = qp.kkt_residuals(g["H"][b], g["f"][b], g["xA"][b], g["lb"][b], g["ub"][b], g["lbA"][b], g["ubA"][b],
+                             o["x"][b], o["lam"][b])
+        assert max(k["primal"], k["stationarity"], k["complementarity"]) < 1e-7
+
+
+def test_dense_qp_on_reference_condensed_dynamic(mpc):
+    g = load_golden("reference_m_dynamic_fss2019.npz")
+    o = mpc.qpOASES(g["H"], g["f"], g["xA"], g["lb"], g["ub"], g["lbA"], g["ubA"])
+    assert (o["exitflag"] == 0).all()
+    nU = g["u_opt"].shape[1]
+    scale = np.maximum(1.0, np.abs(g["u_opt"]).max(axis=1))
+    assert (np.abs(o["x"][:, :nU] - g["u_opt"]).max(axis=1) / scale).max() < 1e-6
+
+
+def test_dense_qp_random_and_infeasible(mpc):
+    from oracle import qp
+    rng = np.random.default_rng(11)
+    B, n, m = 24, 12, 20
+    H = np.empty((B, n, n)); g = rng.normal(size=(B, n)) * 3
+    A = rng.normal(size=(B, m, n))
+    for b in range(B):
+        G = rng.normal(size=(n, n))
+        H[b] = G @ G.T + 0.5 * np.eye(n)
+    lb, ub = -np.ones((B, n)), np.ones((B, n))
+    lbA, ubA = -0.5 * np.ones((B, m)), 0.8 * np.ones((B, m))
+    # last two problems: contradictory rows -> infeasible
+    A[-1, 0] = 0; A[-1, 0, 0] = 1; lbA[-1, 0] = 5; ubA[-1, 0] = 6
+    A[-2, 1] = A[-2, 0]; lbA[-2, 0] = 0.3; ubA[-2, 0] = 0.4; lbA[-2, 1] = -0.4; ubA[-2, 1] = -0.3
+    o = mpc.qpOASES(H, g, A, lb, ub, lbA, ubA)
+    for b in range(B):
+        sol = qp.qpoases(H[b], g[b], A[b], lb[b], ub[b], lbA[b], ubA[b])
+        assert o["exitflag"][b] == sol.exitflag, b
+        if sol.exitflag == 0:
+            assert np.abs(o["x"][b] - sol.x).max() < 1e-8
+            assert np.abs(o["lam"][b] - sol.lam).max() < 1e-6 * (1 + np.abs(sol.lam).max())
+    assert o["exitflag"][-1] == -2 and o["exitflag"][-2] == -2
+
+
+def test_dense_qp_bounds_only_and_too_large(mpc):
+    import fsae_mpc_b200 as fm
+    rng = np.random.default_rng(3)
+    B, n = 4, 7
+    H = np.tile(np.eye(n) * 2, (B, 1, 1)); g = rng.normal(size=(B, n)) * 4
+    o = mpc.qpOASES(H, g, None, -np.ones((B, n)), np.ones((B, n)), None, None)
+    assert np.allclose(o["x"], np.clip(-g / 2, -1, 1), atol=1e-12)
+    with pytest.raises(fm.FsaeError):
+        mpc.qpOASES(np.tile(np.eye(120), (1, 1, 1)), np.zeros((1, 120)), None, -np.ones((1, 120)), np.ones((1, 120)), None, None)

@@ -162,3 +162,25 @@ def test_kernel_variants_agree(mpc):
     assert np.abs(r2.slack_opt - r1.slack_opt).max() < 1e-9
     same = (r1.workingSetB == r2.workingSetB).all(axis=1) & (r1.workingSetC == r2.workingSetC).all(axis=1)
     assert same.mean() > 0.99
+
+
+def test_sqp_passes_match_oracle_loop(mpc, fso):
+    """BASELINE configs[3]: repeated relinearise+QP on fso2020, against the oracle iterated the
+    same way (x_lin, u_lin <- previous x_opt, u_opt)."""
+    import fsae_mpc_b200 as fm
+    from oracle import ltv
+    g = load_golden("kinematic_lap_fso2020.npz")
+    pick = [2, 11, 25, 40]
+    B = len(pick)
+    n_sqp = 3
+    r = mpc.ltvmpc_sqp(fm.KINEMATIC, g["x0"][pick], c_layout(g["x_ref"][pick]), DT, c_layout(g["x_lin"][pick]),
+                       c_layout(g["u_lin"][pick]), n_sqp, track_id=np.full(B, 2, np.int32))
+    assert (r.exitflag == 0).all()
+    for j, b in enumerate(pick):
+        xl, ul = g["x_lin"][b], g["u_lin"][b]
+        for _ in range(n_sqp):
+            u, x, ef, fv, sl, _s = ltv.ltvmpc_kinetmatic_curvilinear(g["x0"][b], g["x_ref"][b], fso.kappa, DT, xl, ul)
+            assert ef == 0
+            xl, ul = x.reshape(5, 40, order="F"), u.reshape(2, 40, order="F")
+        assert rel(r.u_opt[j], u) <= 1e-6 and rel(r.x_opt[j], x) <= 1e-6
+        assert abs(r.fval[j] - fv) <= 1e-6 * (1 + abs(fv))
