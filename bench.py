@@ -265,8 +265,15 @@ def run_ours(args, rank, local_rank, world):
     kms = float(np.mean(kern_ms))
     ach_tf = flops_launch / (kms * 1e-3) / 1e12
     alg_bytes = B * 8 * (NX + 2 * NX * N + NU * N + nU + NX * N + NS + 2) + B * 4
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tp) and B == 65536:
+        with open(tp) as fh:
+            tj = json.load(fh)
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        traffic_src = tj["source"]
     roof = {"bound": "fp64_fma", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": None,
+            "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": "measured in this run (fsae_probe_fp64_tflops, DFMA streams on all SMs)",
             "kernel": "ltvmpc_fused_kernel", "kernel_ms": kms,
             "algorithmic_flops_per_launch": flops_launch,
