@@ -69,6 +69,7 @@ struct DenseProb {
         return sg * A[(size_t)S.perm[i] * nC + (pslot - nV)];
     }
     __device__ __forceinline__ double norm2(int) const { return 1.0; }
+    __device__ __forceinline__ bool is_unit(int pslot) const { return pslot < nV; }
 };
 
 template <int NVMAX>

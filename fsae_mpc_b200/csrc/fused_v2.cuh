@@ -35,8 +35,9 @@ struct SmemV2 {
     double Ad[N * C::NREAL * D::NX];
     double B1[D::NX * D::NU];
     double xf[N * D::NX];
-    double xl[N * D::NX];
-    double ul[N * D::NU];
+    alignas(16) double xl[N * D::NX];  // TMA bulk-copy destinations (16-byte aligned, sizes % 16 == 0)
+    alignas(16) double xr[N * D::NX];
+    alignas(16) double ul[N * D::NU];
     double pc[N * C::NPC];
     double g0[N * C::NG0];
     double cg[C::NCG];
@@ -44,7 +45,29 @@ struct SmemV2 {
     double rn2[D::NROWS];              // squared norm of each row's normal (linear-dependence test)
     double dd[N * D::NX];
     double scal[8];                    // 0 cost const
+    alignas(8) unsigned long long mbar; // mbarrier of the input staging
 };
+
+// ---- TMA (bulk async copy) staging of one problem's contiguous input records ----------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    }
+}
 
 // Problem policy of the core for the LTV-MPC QPs: slots [0, nV) are the variable bounds
 // (ltvmpc_*_curvilinear.m:28-29), slots nV + r*N + k the constraint row r at horizon step k
@@ -149,6 +172,7 @@ struct MpcProb {
     __device__ __forceinline__ double norm2(int pslot) const {
         return (pslot < D::nV) ? 1.0 : S.rn2[pslot - D::nV];
     }
+    __device__ __forceinline__ bool is_unit(int pslot) const { return pslot < D::nV; }
 };
 
 template <class Model, int N, int MINB, int NW_ = 8>
@@ -169,14 +193,35 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     const double dt = a.dt;
     const int row0 = warp * RPW;            // first row of this warp
 
-    // ---------------------------------------------------------------- load
+    // ---------------------------------------------------------------- load (TMA bulk copies)
+    // x_lin, u_lin, x_ref of one problem are contiguous records: one elected thread issues
+    // three cp.async.bulk copies that complete on an mbarrier while the other threads clear
+    // the working set.  Misaligned caller pointers fall back to plain loads.
     {
         const double* gxl = a.x_lin + (size_t)b * NX * N;
         const double* gul = a.u_lin + (size_t)b * NU * N;
-        for (int i = tid; i < NX * N; i += NT) S.xl[i] = gxl[i];
-        for (int i = tid; i < NU * N; i += NT) S.ul[i] = gul[i];
+        const double* gxr = a.x_ref + (size_t)b * NX * N;
+        constexpr unsigned BX = NX * N * 8, BU = NU * N * 8;
+        static_assert(BX % 16 == 0 && BU % 16 == 0, "bulk copy sizes must be multiples of 16 bytes");
+        const bool aligned = ((((size_t)gxl) | ((size_t)gul) | ((size_t)gxr)) & 15) == 0;
+        if (aligned) {
+            if (tid == 0) mbar_init(&S.mbar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(&S.mbar, 2 * BX + BU);
+                tma_bulk_g2s(S.xl, gxl, BX, &S.mbar);
+                tma_bulk_g2s(S.ul, gul, BU, &S.mbar);
+                tma_bulk_g2s(S.xr, gxr, BX, &S.mbar);
+            }
+        }
         for (int i = tid; i < D::NSLOT; i += NT) S.gi.status[i] = 0;
         for (int i = tid; i < RP; i += NT) { S.gi.x[i] = 0.0; S.gi.g[i] = 0.0; S.gi.rowv[i] = 0.0; S.gi.nvec[i] = 0.0; S.gi.zrow[i] = 0.0; S.gi.colk[0][i] = 0.0; S.gi.colk[1][i] = 0.0; }
+        if (aligned) {
+            mbar_wait(&S.mbar, 0);
+        } else {
+            for (int i = tid; i < NX * N; i += NT) { S.xl[i] = gxl[i]; S.xr[i] = gxr[i]; }
+            for (int i = tid; i < NU * N; i += NT) S.ul[i] = gul[i];
+        }
     }
     __syncthreads();
 
@@ -259,8 +304,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     // ---------------------------------------------------------------- g, bounds, row norms, cost const
     {
         double* e = S.dd;      // tracking error overwrites dd (dead after the free response)
-        const double* gxr = a.x_ref + (size_t)b * NX * N;
-        for (int i = tid; i < NX * N; i += NT) e[i] = S.xf[i] - gxr[i];
+        for (int i = tid; i < NX * N; i += NT) e[i] = S.xf[i] - S.xr[i];
         __syncthreads();
         for (int j = tid; j < nV; j += NT) {
             double acc = 0.0;

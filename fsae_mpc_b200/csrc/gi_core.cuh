@@ -354,7 +354,9 @@ struct GiOps {
             rbuf ^= 1;
 
             if (!(viol < -tol)) {
-                if (st.n_refresh >= 1) break;
+                // the refresh repairs what chains of partial steps leave behind; a run of pure
+                // full steps keeps x the exact working-set minimiser (to round-off)
+                if (st.n_refresh >= 1 || st.n_drop == 0) break;
                 // refresh: Newton step on the active manifold + multipliers from stationarity
                 ++st.n_refresh;
                 symv_to_rowv(S, S.x, S.g, nV);                       // rowv = H x + g
@@ -387,9 +389,27 @@ struct GiOps {
             bool failed = false;
             while (true) {
                 if (++st.iters > max_iter) { st.exitflag = GI_EXIT_MAXITER; failed = true; break; }
-                // P3: y = M' n
+                // P3: y = M' n.  For a variable bound n = +-e_p, so y is +-(row p of M): the owning
+                // warp publishes its row, nobody multiplies or sums partials.
                 double y[CS], dummy;
-                matvec_T(S, m, ybuf, S.nvec, 0.0, y, dummy);
+                if (prob.is_unit(pslot)) {
+                    const int pr = pslot - row0;               // warp-uniform
+                    if (pr >= 0 && pr < RPW) {
+#pragma unroll
+                        for (int r = 0; r < RPW; ++r)
+                            if (r == pr) {
+#pragma unroll
+                                for (int s = 0; s < CS; ++s) S.ypart[ybuf][0][lane + 32 * s] = m[r][s];
+                            }
+                    }
+                    __syncthreads();
+                    const double sgn = pside < 0 ? 1.0 : -1.0;
+#pragma unroll
+                    for (int s = 0; s < CS; ++s) y[s] = sgn * S.ypart[ybuf][0][lane + 32 * s];
+                    ybuf ^= 1;
+                } else {
+                    matvec_T(S, m, ybuf, S.nvec, 0.0, y, dummy);
+                }
                 // P4 (every warp, redundantly): step lengths
                 double d2 = 0.0, t1 = INFINITY;
                 int l = -1;
@@ -398,7 +418,7 @@ struct GiOps {
                     const int j = lane + 32 * s;
                     if (j >= q && j < nV) d2 += y[s] * y[s];
                     else if (j < q && y[s] > 1e-13) {
-                        const double tj = lam[s] / y[s];
+                        const double tj = lam[s] * __drcp_rn(y[s]);
                         if (tj < t1) { t1 = tj; l = j; }
                     }
                 }
@@ -412,7 +432,8 @@ struct GiOps {
                     t1 = tm;
                 }
                 const bool lin_dep = !(d2 > 1e-13 * fmax(1.0, nn));
-                const double t2 = lin_dep ? INFINITY : (sp < 0.0 ? -sp / d2 : 0.0);
+                const double inv_d2 = __drcp_rn(d2);
+                const double t2 = lin_dep ? INFINITY : (sp < 0.0 ? -sp * inv_d2 : 0.0);
                 if (isinf(t1) && isinf(t2)) { st.exitflag = GI_EXIT_INFEASIBLE; failed = true; break; }
                 const bool full = (t2 <= t1);
                 const bool primal = !isinf(t2);
@@ -454,15 +475,14 @@ struct GiOps {
                             }
                     }
                     __syncwarp();
-                    const double delta = sqrt(d2);
+                    const double delta = d2 * rsqrt(d2);
                     double yq_l = 0.0;
 #pragma unroll
                     for (int s = 0; s < CS; ++s)
                         if (s == qs) yq_l = y[s];
                     const double yq = __shfl_sync(0xffffffffu, yq_l, ql);
                     const double sgd = (yq >= 0.0) ? delta : -delta;
-                    const double beta = 1.0 / (d2 + fabs(yq) * delta);
-                    const double inv_d2 = 1.0 / d2;
+                    const double beta = __drcp_rn(d2 + fabs(yq) * delta);
                     // new = c*cur - kr*ya - wr*yb with (c, ya, yb) = (1, y, 0) for j < q,
                     // (0, -1, 0) for j == q, (1, 0, y) for j > q: no per-element selects
                     double cc[CS], ya[CS], yb[CS];
