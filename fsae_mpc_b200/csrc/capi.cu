@@ -52,6 +52,7 @@ struct fsae_ctx {
     unsigned long long* d_counters = nullptr;
     // staging for *_host calls
     DevBuf in[8], out[12];
+    DevBuf m_scratch[2];       // operator slabs of the long-horizon (global-operator) kernel, per stream
 };
 
 #define CK(call)                                                                       \
@@ -133,6 +134,7 @@ extern "C" int fsae_destroy(fsae_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->in) b.release();
     for (auto& b : ctx->out) b.release();
+    for (auto& b : ctx->m_scratch) b.release();
     for (int i = 0; i < FSAE_MAX_TRACKS; ++i)
         if (ctx->d_coef[i]) cudaFree(ctx->d_coef[i]);
     cudaFree(ctx->d_params);
@@ -362,6 +364,46 @@ static int launch_fused_v1(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
     return FSAE_OK;
 }
 
+// Long horizons (nV > 95: the operator no longer fits one CTA's registers or shared memory):
+// the shared-memory kernel variant with the operator in a per-CTA global slab that stays
+// L2-resident (<= 148 CTAs x 207 KB in flight).  Launched in slices so the slab pool is bounded.
+template <class Model, int N>
+static int launch_fused_long(fsae_ctx* ctx, BatchArgs a, cudaStream_t st) {
+    using S_t = SmemV1<Model, N, 256, true>;
+    using D = Dims<Model, N>;
+    auto kern = ltvmpc_fused_v1_kernel<Model, N, 256, true>;
+    static bool configured[64] = {false};
+    if (!configured[ctx->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S_t)));
+        configured[ctx->device & 63] = true;
+    }
+    constexpr int SLICE = 2048;
+    DevBuf& pool = ctx->m_scratch[st == ctx->stream2 ? 1 : 0];
+    const int nsl = a.B < SLICE ? a.B : SLICE;
+    CK(pool.reserve((size_t)nsl * D::nV * D::LD * sizeof(double)));
+    const int B = a.B;
+    constexpr int NX = Model::NX, NU = Model::NU, NS = Model::NS, nU = NU * N, nV = nU + NS;
+    const int nC = Cons<Model>::n_ref_rows(N);
+    for (int lo = 0; lo < B; lo += SLICE) {
+        BatchArgs c = a;
+        c.B = (lo + SLICE <= B) ? SLICE : B - lo;
+        c.m_scratch = (double*)pool.p;
+        if (a.track_id) c.track_id = a.track_id + lo;
+        if (a.param_id) c.param_id = a.param_id + lo;
+        c.x0 = a.x0 + (size_t)lo * NX; c.x_ref = a.x_ref + (size_t)lo * NX * N;
+        c.x_lin = a.x_lin + (size_t)lo * NX * N; c.u_lin = a.u_lin + (size_t)lo * NU * N;
+        c.u_opt = a.u_opt + (size_t)lo * nU; c.x_opt = a.x_opt + (size_t)lo * NX * N;
+        c.exitflag = a.exitflag + lo; c.fval = a.fval + lo; c.slack_opt = a.slack_opt + (size_t)lo * NS;
+        if (a.iters) c.iters = a.iters + lo;
+        if (a.wsB) c.wsB = a.wsB + (size_t)lo * nV;
+        if (a.wsC) c.wsC = a.wsC + (size_t)lo * nC;
+        kern<<<c.B, 256, sizeof(S_t), st>>>(c);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    return FSAE_OK;
+}
+
 template <class Model, int N, int MINB, int NW = 8>
 static int launch_fused_v2(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
     using S_t = SmemV2<Model, N, NW>;
@@ -405,7 +447,8 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
         const bool v1 = ctx->kernel_version == 1;
         if (N == 40) rc = v1 ? launch_fused_v1<KinModel, 40, 256>(ctx, a, st) : launch_fused_v2<KinModel, 40, 2>(ctx, a, st);
         else if (N == 20) rc = v1 ? launch_fused_v1<KinModel, 20, 256>(ctx, a, st) : launch_fused_v2<KinModel, 20, 2>(ctx, a, st);
-        else ctx->err = "kinematic fused step: horizon must be 20 or 40";
+        else if (N == 80) rc = launch_fused_long<KinModel, 80>(ctx, a, st);
+        else ctx->err = "kinematic fused step: horizon must be 20, 40 or 80";
     } else {
         if (N == 40) rc = launch_fused_v2<DynModel, 40, 1>(ctx, a, st);
         else if (N == 20) rc = launch_fused_v2<DynModel, 20, 1>(ctx, a, st);

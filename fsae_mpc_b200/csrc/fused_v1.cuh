@@ -39,6 +39,7 @@ struct BatchArgs {
     double* dbg_H;
     double* dbg_g;
     unsigned long long* counters;   // [0] adds, [1] drops, [2] refreshes (atomicAdd per problem)
+    double* m_scratch;              // per-CTA operator slabs for the long-horizon (global-operator) variant
 };
 
 template <class Model, int N_>
@@ -56,12 +57,12 @@ struct Dims {
     __host__ __device__ static constexpr int hp(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
 };
 
-template <class Model, int N, int NT>
+template <class Model, int N, int NT, bool MG = false>
 struct SmemV1 {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
     static constexpr int NW = NT / 32;
-    double M[D::nV * D::LD];
+    double M[MG ? 1 : D::nV * D::LD];   // MG: the operator lives in a per-CTA global (L2) slab instead
     double Hp[D::HP];
     double Bc[C::NCR * D::NPK];
     double Ad[N * C::NREAL * D::NX];
@@ -116,8 +117,16 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// operator element load: shared memory, or (global-operator variant) an L1-bypassing global load
+// so that values written by other warps of the CTA before a barrier are always observed
+template <bool MG>
+__device__ __forceinline__ double ldM(const double* p) {
+    if constexpr (MG) return __ldcg(p);
+    else return *p;
+}
+
 // y = M^T v over all columns: thread (j, part) partial sums; caller syncs then sums 3 parts.
-template <class D, int NT>
+template <class D, int NT, bool MG = false>
 __device__ __forceinline__ void matvec_T_parts(const double* M, const double* v, double* part) {
     constexpr int nV = D::nV, LD = D::LD;
     constexpr int CH = (nV + 2) / 3;
@@ -125,13 +134,13 @@ __device__ __forceinline__ void matvec_T_parts(const double* M, const double* v,
         const int pt = t / nV, j = t - pt * nV;
         const int i0 = pt * CH, i1 = (i0 + CH < nV) ? i0 + CH : nV;
         double acc = 0.0;
-        for (int i = i0; i < i1; ++i) acc += M[i * LD + j] * v[i];
+        for (int i = i0; i < i1; ++i) acc += ldM<MG>(&M[i * LD + j]) * v[i];
         part[pt * nV + j] = acc;
     }
 }
 
 // z = M[:, q:] * y[q:]: thread (i, part) partial sums over a third of the column range.
-template <class D, int NT>
+template <class D, int NT, bool MG = false>
 __device__ __forceinline__ void matvec_N_parts(const double* M, const double* y, int q, double* part) {
     constexpr int nV = D::nV, LD = D::LD;
     const int span = nV - q;
@@ -141,7 +150,7 @@ __device__ __forceinline__ void matvec_N_parts(const double* M, const double* y,
         const int j0 = q + pt * CH;
         const int j1 = (j0 + CH < nV) ? j0 + CH : nV;
         double acc = 0.0;
-        for (int j = j0; j < j1; ++j) acc += M[i * LD + j] * y[j];
+        for (int j = j0; j < j1; ++j) acc += ldM<MG>(&M[i * LD + j]) * y[j];
         part[pt * nV + i] = acc;
     }
 }
@@ -159,8 +168,8 @@ __device__ __forceinline__ void symv_packed(const double* Hp, const double* v, d
 }
 
 // constraint-state perturbations xs[c][k] = (B_bar x_u)[state c, step k]
-template <class Model, int N, int NT>
-__device__ __forceinline__ void eval_xs(const SmemV1<Model, N, NT>& S, const double* x, double dt,
+template <class Model, int N, int NT, bool MG>
+__device__ __forceinline__ void eval_xs(const SmemV1<Model, N, NT, MG>& S, const double* x, double dt,
                                         double* xs) {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
@@ -181,8 +190,8 @@ __device__ __forceinline__ void eval_xs(const SmemV1<Model, N, NT>& S, const dou
 }
 
 // entry j of the GI normal of (slot, side):  n'x >= b  form
-template <class Model, int N, int NT>
-__device__ __forceinline__ double normal_entry(const SmemV1<Model, N, NT>& S, int slot, int side,
+template <class Model, int N, int NT, bool MG>
+__device__ __forceinline__ double normal_entry(const SmemV1<Model, N, NT, MG>& S, int slot, int side,
                                                int j, double dt) {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
@@ -207,11 +216,11 @@ __device__ __forceinline__ double normal_entry(const SmemV1<Model, N, NT>& S, in
     return sg * v;
 }
 
-template <class Model, int N, int NT>
+template <class Model, int N, int NT, bool MG = false>
 __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
-    using S_t = SmemV1<Model, N, NT>;
+    using S_t = SmemV1<Model, N, NT, MG>;
     constexpr int NX = D::NX, NU = D::NU, NS = D::NS, nU = D::nU, nV = D::nV, LD = D::LD;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S_t& S = *reinterpret_cast<S_t*>(smem_raw);
@@ -222,6 +231,7 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
     const DevTrack tr = a.tracks[a.track_id ? a.track_id[b] : 0];
     const double dt = a.dt;
     const int scheme = P.lin_scheme;
+    double* const Mop = MG ? (a.m_scratch + (size_t)b * D::nV * D::LD) : S.M;
 
     // ---------------------------------------------------------------- load
     {
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
     __syncthreads();
 
     // ---------------------------------------------------------------- free response + B_bar chains
-    double* Bf = S.M;               // NREAL packed rows, lives in M until H is built
+    double* Bf = Mop;               // NREAL packed rows, lives in M until H is built
     static_assert(C::NREAL * D::NPK <= nV * LD, "packed B_bar does not fit the M region");
     if (warp == NT / 32 - 1) {
         // xf_k = Ad_k xf_{k-1} + dd_k, xf_{-1} = x0   (A_bar x0 + d_bar, sequential_integration.m:21-26,38-47)
@@ -342,7 +352,7 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
                     for (int ii = 0; ii < C::NREAL; ++ii) {
                         const int r = C::real_state(ii);
                         const double q = (k == N - 1) ? P.Q_terminal[r] : P.Q[r];
-                        s += q * Bf[ii * D::NPK + D::pk(k, i)] * Bf[ii * D::NPK + D::pk(k, j)];
+                        s += q * ldM<MG>(&Bf[ii * D::NPK + D::pk(k, i)]) * ldM<MG>(&Bf[ii * D::NPK + D::pk(k, j)]);
                     }
                     acc += s;
                 }
@@ -370,7 +380,7 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
                     for (int ii = 0; ii < C::NREAL; ++ii) {
                         const int r = C::real_state(ii);
                         const double q = (k == N - 1) ? P.Q_terminal[r] : P.Q[r];
-                        acc += q * Bf[ii * D::NPK + D::pk(k, j)] * e[k * NX + r];
+                        acc += q * ldM<MG>(&Bf[ii * D::NPK + D::pk(k, j)]) * e[k * NX + r];
                     }
 #pragma unroll
                     for (int ii = 0; ii < C::NINT; ++ii) {
@@ -409,7 +419,7 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
         // keep the constraint rows of B_bar
         for (int t = tid; t < C::NCR * D::NPK; t += NT) {
             const int c = t / D::NPK, o = t - c * D::NPK;
-            S.Bc[t] = Bf[C::cons_real(c) * D::NPK + o];
+            S.Bc[t] = ldM<MG>(&Bf[C::cons_real(c) * D::NPK + o]);
         }
     }
     __syncthreads();
@@ -429,17 +439,18 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
     // Working storage: MU(i,j) = M[i*LD + NS + j], i,j < nU.  Lower triangle of the active
     // trailing block holds the Schur complement; eliminated columns hold X = L1^-1 (unit lower).
     __syncthreads();
-#define MU(i, j) S.M[(i) * LD + NS + (j)]
+#define MU(i, j) Mop[(i) * LD + NS + (j)]
+#define MUL(i, j) ldM<MG>(&Mop[(i) * LD + NS + (j)])
     for (int t = tid; t < nU * nU; t += NT) {
         const int i = t / nU, j = t - i * nU;
         MU(i, j) = (i >= j) ? S.Hp[D::hp(i, j)] : 0.0;
     }
     __syncthreads();
     for (int k = 0; k < nU; ++k) {
-        const double piv = MU(k, k);
+        const double piv = MUL(k, k);
         const double rp = 1.0 / piv;
         for (int i = k + 1 + tid; i < nU; i += NT) {
-            const double cik = MU(i, k);
+            const double cik = MUL(i, k);
             S.z[i] = cik;                 // column k of the Schur complement
             S.kv[i] = cik * rp;           // multipliers l_i
         }
@@ -450,16 +461,16 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
         for (int t = tid; t < rows * nU; t += NT) {
             const int i = k + 1 + t / nU, j = t % nU;
             const double li = S.kv[i];
-            if (j < k) MU(i, j) -= li * MU(k, j);
+            if (j < k) MU(i, j) = MUL(i, j) - li * MUL(k, j);
             else if (j == k) MU(i, k) = -li;
-            else if (j <= i) MU(i, j) -= li * S.z[j];
+            else if (j <= i) MU(i, j) = MUL(i, j) - li * S.z[j];
         }
         __syncthreads();
     }
     // J = L^-T: J[r][c] = X[c][r] / sqrt(d_c)  (r <= c), zero below.  In place: upper <- lower^T.
     for (int t = tid; t < nU * nU; t += NT) {
         const int c = t / nU, r = t - c * nU;      // c >= r pairs only
-        if (r < c) MU(r, c) = MU(c, r) * rsqrt(S.dvec[c]);
+        if (r < c) MU(r, c) = MUL(c, r) * rsqrt(S.dvec[c]);
     }
     __syncthreads();
     for (int t = tid; t < nU * nU; t += NT) {
@@ -470,13 +481,14 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
     // slack rows/columns: K1 columns 0..NS-1 = e_{nU+k}; slack rows of J2 are zero
     for (int t = tid; t < nV * NS; t += NT) {
         const int i = t / NS, k = t - i * NS;
-        S.M[i * LD + k] = (i == nU + k) ? 1.0 : 0.0;
+        Mop[i * LD + k] = (i == nU + k) ? 1.0 : 0.0;
     }
     for (int t = tid; t < NS * nU; t += NT) {
         const int k = t / nU, j = t - k * nU;
-        S.M[(nU + k) * LD + NS + j] = 0.0;
+        Mop[(nU + k) * LD + NS + j] = 0.0;
     }
 #undef MU
+#undef MUL
     if (tid < NS) {
         S.act[tid] = (nU + tid) * 2;            // slack lower bound active
         S.lam[tid] = S.g[nU + tid];
@@ -491,11 +503,11 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
     __syncthreads();
 
     // ---------------------------------------------------------------- x0 = -J2 J2' g ; slack at 0
-    matvec_T_parts<D, NT>(S.M, S.g, S.part);
+    matvec_T_parts<D, NT, MG>(Mop, S.g, S.part);
     __syncthreads();
     for (int j = tid; j < nV; j += NT) S.y[j] = S.part[j] + S.part[nV + j] + S.part[2 * nV + j];
     __syncthreads();
-    matvec_N_parts<D, NT>(S.M, S.y, NS, S.part);
+    matvec_N_parts<D, NT, MG>(Mop, S.y, NS, S.part);
     __syncthreads();
     for (int i = tid; i < nV; i += NT)
         S.x[i] = (i < nU) ? -(S.part[i] + S.part[nV + i] + S.part[2 * nV + i]) : 0.0;
@@ -507,7 +519,7 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
     unsigned long long n_add = 0, n_drop = 0;
     while (true) {
         // P1: most violated inactive constraint side
-        eval_xs<Model, N, NT>(S, S.x, dt, S.xs);
+        eval_xs<Model, N, NT, MG>(S, S.x, dt, S.xs);
         __syncthreads();
         double best = 0.0;
         int best_i = 0x7fffffff;
@@ -546,11 +558,11 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
             __syncthreads();
             for (int i = tid; i < nV; i += NT) S.wv[i] += S.g[i];
             __syncthreads();
-            matvec_T_parts<D, NT>(S.M, S.wv, S.part);
+            matvec_T_parts<D, NT, MG>(Mop, S.wv, S.part);
             __syncthreads();
             for (int j = tid; j < nV; j += NT) S.y[j] = S.part[j] + S.part[nV + j] + S.part[2 * nV + j];
             __syncthreads();
-            matvec_N_parts<D, NT>(S.M, S.y, q, S.part);
+            matvec_N_parts<D, NT, MG>(Mop, S.y, q, S.part);
             __syncthreads();
             double dxm = 0.0;
             for (int i = tid; i < nV; i += NT) {
@@ -568,14 +580,14 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
         }
         const int pslot = pcode >> 1, pside = (pcode & 1) ? +1 : -1;
         // P2: normal
-        for (int j = tid; j < nV; j += NT) S.nv[j] = normal_entry<Model, N, NT>(S, pslot, pside, j, dt);
+        for (int j = tid; j < nV; j += NT) S.nv[j] = normal_entry<Model, N, NT, MG>(S, pslot, pside, j, dt);
         if (tid == 0) S.sc[5] = 0.0;     // multiplier of p
         __syncthreads();
         bool done_p = false;
         while (!done_p) {
             const int q = S.isc[0];
             // P3: y = M' n
-            matvec_T_parts<D, NT>(S.M, S.nv, S.part);
+            matvec_T_parts<D, NT, MG>(Mop, S.nv, S.part);
             __syncthreads();
             // P4: warp 0 combines and decides the step
             if (warp == 0) {
@@ -641,7 +653,7 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
             const double t = S.sc[0];
             // P5: primal step direction z = J2 y2
             if (type != STEP_DUAL) {
-                matvec_N_parts<D, NT>(S.M, S.y, q, S.part);
+                matvec_N_parts<D, NT, MG>(Mop, S.y, q, S.part);
                 __syncthreads();
                 const double d2 = S.sc[1], sgd = S.sc[2];
                 for (int i = tid; i < nV; i += NT) {
@@ -649,7 +661,7 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
                     S.x[i] += t * zi;
                     if (type == STEP_FULL) {
                         S.kv[i] = zi / d2;
-                        S.wv[i] = zi + sgd * S.M[i * LD + q];
+                        S.wv[i] = zi + sgd * ldM<MG>(&Mop[i * LD + q]);
                     }
                 }
             }
@@ -661,11 +673,11 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
                 const double beta = S.sc[3], sgd = S.sc[2];
                 for (int tt = tid; tt < nV * nV; tt += NT) {
                     const int i = tt / nV, j = tt - i * nV;
-                    double m = S.M[i * LD + j];
+                    double m = ldM<MG>(&Mop[i * LD + j]);
                     if (j < q) m -= S.kv[i] * S.y[j];
                     else if (j == q) m = S.kv[i];
                     else m -= beta * S.wv[i] * S.y[j];
-                    S.M[i * LD + j] = m;
+                    Mop[i * LD + j] = m;
                 }
                 (void)sgd;
                 if (tid == 0) {
@@ -680,11 +692,11 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
             } else {
                 // P6b: drop active constraint l
                 const int l = S.isc[4];
-                for (int i = tid; i < nV; i += NT) S.kv[i] = S.M[i * LD + l];
+                for (int i = tid; i < nV; i += NT) S.kv[i] = ldM<MG>(&Mop[i * LD + l]);
                 __syncthreads();
                 symv_packed<D, NT>(S.Hp, S.kv, S.wv);
                 __syncthreads();
-                matvec_T_parts<D, NT>(S.M, S.wv, S.part);     // all columns; only j<q, j!=l used
+                matvec_T_parts<D, NT, MG>(Mop, S.wv, S.part);     // all columns; only j<q, j!=l used
                 if (warp == 0) {
                     double acc = 0.0;
                     for (int i = lane; i < nV; i += 32) acc += S.kv[i] * S.wv[i];
@@ -698,13 +710,13 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
                 __syncthreads();
                 for (int tt = tid; tt < nV * q; tt += NT) {
                     const int i = tt / q, j = tt - i * q;
-                    if (j != l) S.M[i * LD + j] += S.kv[i] * S.z[j];
+                    if (j != l) Mop[i * LD + j] = ldM<MG>(&Mop[i * LD + j]) + S.kv[i] * S.z[j];
                 }
                 __syncthreads();
                 const double rs = rsqrt(kHk);
                 for (int i = tid; i < nV; i += NT) {
-                    if (l != q - 1) S.M[i * LD + l] = S.M[i * LD + q - 1];
-                    S.M[i * LD + q - 1] = S.kv[i] * rs;
+                    if (l != q - 1) Mop[i * LD + l] = ldM<MG>(&Mop[i * LD + q - 1]);
+                    Mop[i * LD + q - 1] = S.kv[i] * rs;
                 }
                 if (tid == 0) {
                     S.status[S.act[l] >> 1] = 0;

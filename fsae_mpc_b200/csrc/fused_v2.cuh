@@ -86,7 +86,8 @@ struct MpcProb {
     // states) and split that step's rows among themselves; threads [4N, 4N+nV): the bounds.
     __device__ __forceinline__ void search(double& best, int& best_i) const {
         constexpr int NU = D::NU, nU = D::nU, nV = D::nV, NT = G::NT;
-        static_assert(4 * N + nV <= NT, "P1 thread map needs 4N + nV <= threads per CTA");
+        constexpr int ROWT = ((4 * N + 31) / 32) * 32;      // row threads, rounded up to whole warps
+        static_assert(ROWT + nV <= NT, "P1 thread map needs ceil32(4N) + nV <= threads per CTA");
         static_assert(NU == 2, "paired (double2) row loads assume two controls per step");
         const int tid = threadIdx.x, warp = tid >> 5;
         const double* x = S.gi.x;
@@ -133,7 +134,7 @@ struct MpcProb {
                 }
             }
         } else {
-            const int slot = tid - 4 * N;
+            const int slot = tid - ROWT;
             if (slot >= 0 && slot < nV && S.gi.status[slot] == 0) {
                 const double xv = x[slot];
                 const double lb = (slot < nU) ? P.u_lb[slot % NU] : 0.0;

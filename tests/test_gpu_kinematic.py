@@ -184,3 +184,12 @@ def test_sqp_passes_match_oracle_loop(mpc, fso):
             xl, ul = x.reshape(5, 40, order="F"), u.reshape(2, 40, order="F")
         assert rel(r.u_opt[j], u) <= 1e-6 and rel(r.x_opt[j], x) <= 1e-6
         assert abs(r.fval[j] - fv) <= 1e-6 * (1 + abs(fv))
+
+
+@pytest.mark.parametrize("N", [20, 80])
+def test_other_horizons_match_golden(mpc, N):
+    """BASELINE configs[4]: horizons 20 and 80 (80: nV = 161, the operator lives in an
+    L2-resident global slab instead of registers)."""
+    g = load_golden(f"kinematic_lap_fsg2019_N{N}.npz")
+    r = mpc.ltvmpc_kinetmatic_curvilinear(g["x0"], c_layout(g["x_ref"]), DT, c_layout(g["x_lin"]), c_layout(g["u_lin"]))
+    _check_solution(r, g)
