@@ -58,6 +58,8 @@ SIGNATURES = {
                                    _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _dp, _ip, _bp, _bp]),
     "fsae_ltvmpc_sqp_host": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _ip, _ip,
                                        _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _dp, _ip]),
+    "fsae_closed_loop_host": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, _ip, _ip,
+                                        _dp, _dp, _dp, _dp, _ip, _dp, _dp, _ip]),
     "fsae_ltvmpc_dev": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -244,6 +244,32 @@ class FsaeMpc:
             "fsae_ltvmpc_sqp_host")
         return r
 
+    def closed_loop(self, model, plant0, n_sim, N=40, dt=0.05, target_vel=20.0, x_opt0=None, u_opt0=None,
+                    track_id=None, param_id=None, history=True):
+        """main.m's closed loop for B vehicles (fsae_closed_loop_host).  plant0 (B,7).  The default
+        initial guess is main.m:42-53 (quadratic arc length, linear speed, constant 10 m/s^2).
+        Returns dict(plant, steps, n_hist (B,n_sim), plant_hist (B,n_sim,7), exit_hist)."""
+        NX, NU, NS = _DIMS[model]
+        plant0 = np.ascontiguousarray(plant0, dtype=np.float64)
+        B = plant0.shape[0]
+        plant0 = _f64(plant0, (B, 7))
+        if x_opt0 is None:
+            t = dt * np.arange(1, N + 1)
+            x1 = np.zeros((N, NX)); x1[:, 0] = 10 * t ** 2 / 2; x1[:, 3] = 10 * t
+            u1 = np.zeros((N, NU)); u1[:, 0] = 10
+            x_opt0 = np.tile(x1[None], (B, 1, 1)); u_opt0 = np.tile(u1[None], (B, 1, 1))
+        x_opt0 = _f64(x_opt0, (B, N, NX)); u_opt0 = _f64(u_opt0, (B, N, NU))
+        t_, p_ = self._ids(B, track_id, param_id)
+        o = dict(plant=np.empty((B, 7)), steps=np.empty(B, np.int32))
+        if history:
+            o.update(n_hist=np.empty((B, n_sim)), plant_hist=np.empty((B, n_sim, 7)), exit_hist=np.empty((B, n_sim), np.int32))
+        self._check(self._lib.fsae_closed_loop_host(
+            self._ctx, model, B, int(N), float(dt), int(n_sim), float(target_vel), _ip(t_), _ip(p_),
+            _dp(plant0), _dp(x_opt0), _dp(u_opt0), _dp(o["plant"]), _ip(o["steps"]),
+            _dp(o["n_hist"]) if history else None, _dp(o["plant_hist"]) if history else None,
+            _ip(o["exit_hist"]) if history else None), "fsae_closed_loop_host")
+        return o
+
     def ltvmpc_dev(self, model, B, N, dt, ptrs, stream=0):
         """Device-pointer entry (fsae_ltvmpc_dev).  `ptrs` is a dict of integer device
         addresses: x0,x_ref,x_lin,u_lin,u_opt,x_opt,exitflag,fval,slack_opt and optionally

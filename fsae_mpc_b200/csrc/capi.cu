@@ -13,6 +13,7 @@
 #include "staged.cuh"
 #include "probe.cuh"
 #include "dense_qp.cuh"
+#include "closed_loop.cuh"
 
 using namespace fsae;
 
@@ -48,6 +49,7 @@ struct fsae_ctx {
     fsae_params* d_params = nullptr;
     DevTrack h_tracks[FSAE_MAX_TRACKS];
     double* d_coef[FSAE_MAX_TRACKS];
+    double track_len[FSAE_MAX_TRACKS];
     DevTrack* d_tracks = nullptr;
     unsigned long long* d_counters = nullptr;
     // staging for *_host calls
@@ -189,6 +191,7 @@ extern "C" int fsae_set_track(fsae_ctx* ctx, int track_id, const double* x_splin
     ctx->h_tracks[track_id].coef = ctx->d_coef[track_id];
     ctx->h_tracks[track_id].n_seg = n_seg;
     ctx->h_tracks[track_id].dl = dl;
+    ctx->track_len[track_id] = dl * n_seg;       // arclength_reparam.m:29,64: L = M * dl
     CK(cudaMemcpy(ctx->d_tracks + track_id, &ctx->h_tracks[track_id], sizeof(DevTrack), cudaMemcpyHostToDevice));
     return FSAE_OK;
 }
@@ -636,6 +639,89 @@ extern "C" int fsae_qpoases_host(fsae_ctx* ctx, int B, int nV, int nC,
     for (int i = 0; i < 7; ++i)
         if (dst[i] && (i != 6 || nC)) CK(cudaMemcpyAsync(dst[i], ctx->out[i].p, szo[i], cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return FSAE_OK;
+}
+
+extern "C" int fsae_closed_loop_host(fsae_ctx* ctx, int model, int B, int N, double dt, int n_sim,
+                                     double target_vel, const int32_t* track_id, const int32_t* param_id,
+                                     const double* plant0, const double* x_opt0, const double* u_opt0,
+                                     double* plant_final, int32_t* steps,
+                                     double* n_hist, double* plant_hist, int32_t* exit_hist) {
+    int NX, NU, NS;
+    if (!ctx || model_dims(model, NX, NU, NS) != FSAE_OK || B < 0 || n_sim < 1 || !plant0 || !x_opt0 || !u_opt0 ||
+        !plant_final || !steps)
+        return FSAE_ERR_ARG;
+    if (B == 0) return FSAE_OK;
+    int rc = check_ids(ctx, B, track_id, param_id);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int nU = NU * N, nXN = NX * N;
+    const int32_t *d_tid, *d_pid;
+    rc = upload_ids(ctx, B, track_id, param_id, &d_tid, &d_pid);
+    if (rc) return rc;
+    // in[0] x0, in[1] x_ref, in[2]/out[9] x_opt ping-pong, in[3]/out[8] u_opt ping-pong
+    const size_t sz_x0 = (size_t)B * NX * 8, sz_x = (size_t)B * nXN * 8, sz_u = (size_t)B * nU * 8;
+    CK(ctx->in[0].reserve(sz_x0)); CK(ctx->in[1].reserve(sz_x)); CK(ctx->in[2].reserve(sz_x)); CK(ctx->in[3].reserve(sz_u));
+    CK(ctx->out[0].reserve(sz_u)); CK(ctx->out[1].reserve(sz_x)); CK(ctx->out[2].reserve((size_t)B * 4));
+    CK(ctx->out[3].reserve((size_t)B * 8)); CK(ctx->out[4].reserve((size_t)B * NS * 8)); CK(ctx->out[5].reserve((size_t)B * 4));
+    DevBuf plant, pid, alive, stepsb, nh, ph, eh;
+    auto cleanup = [&]() { plant.release(); pid.release(); alive.release(); stepsb.release(); nh.release(); ph.release(); eh.release(); };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); return FSAE_ERR_CUDA; } } while (0)
+    CKC(plant.reserve((size_t)B * 7 * 8)); CKC(pid.reserve((size_t)B * 4 * 8)); CKC(alive.reserve((size_t)B * 4)); CKC(stepsb.reserve((size_t)B * 4));
+    if (n_hist) CKC(nh.reserve((size_t)B * n_sim * 8));
+    if (plant_hist) CKC(ph.reserve((size_t)B * n_sim * 7 * 8));
+    if (exit_hist) CKC(eh.reserve((size_t)B * n_sim * 4));
+    CKC(cudaMemcpyAsync(plant.p, plant0, (size_t)B * 7 * 8, cudaMemcpyHostToDevice, st));
+    CKC(cudaMemcpyAsync(ctx->in[2].p, x_opt0, sz_x, cudaMemcpyHostToDevice, st));
+    CKC(cudaMemcpyAsync(ctx->in[3].p, u_opt0, sz_u, cudaMemcpyHostToDevice, st));
+    CKC(cudaMemsetAsync(pid.p, 0, (size_t)B * 4 * 8, st));
+    CKC(cudaMemsetAsync(stepsb.p, 0, (size_t)B * 4, st));
+    if (n_hist) CKC(cudaMemsetAsync(nh.p, 0, (size_t)B * n_sim * 8, st));
+    if (plant_hist) CKC(cudaMemsetAsync(ph.p, 0, (size_t)B * n_sim * 7 * 8, st));
+    if (exit_hist) CKC(cudaMemsetAsync(eh.p, 0, (size_t)B * n_sim * 4, st));
+    {
+        std::vector<int32_t> ones(B, 1);
+        CKC(cudaMemcpyAsync(alive.p, ones.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+        CKC(cudaStreamSynchronize(st));
+    }
+    SimArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.N = N; a.model = model; a.dt = dt; a.target_vel = target_vel; a.ramp = 10.0;
+    a.track_id = d_tid; a.param_id = d_pid; a.tracks = ctx->d_tracks; a.params = ctx->d_params;
+    a.plant = (double*)plant.p; a.pid = (double*)pid.p; a.alive = (int32_t*)alive.p;
+    a.x0 = (double*)ctx->in[0].p; a.x_ref = (double*)ctx->in[1].p;
+    a.n_hist = n_hist ? (double*)nh.p : nullptr; a.plant_hist = plant_hist ? (double*)ph.p : nullptr;
+    a.exit_hist = exit_hist ? (int32_t*)eh.p : nullptr; a.steps = (int32_t*)stepsb.p;
+    for (int i = 0; i < FSAE_MAX_TRACKS; ++i) a.track_len[i] = ctx->track_len[i];
+    a.n_sim = n_sim;
+    const double* xl = (const double*)ctx->in[2].p;
+    const double* ul = (const double*)ctx->in[3].p;
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    for (int step = 0; step <= n_sim; ++step) {
+        a.step = step; a.do_plant = step > 0; a.x_opt = xl; a.exitflag = step > 0 ? (const int32_t*)ctx->out[2].p : nullptr;
+        sim_advance_kernel<<<grid, 128, 0, st>>>(a);
+        ctx->launches++;
+        CKC(cudaGetLastError());
+        if (step == n_sim) break;
+        double* uo = (double*)((step & 1) ? ctx->out[8].p : ctx->out[0].p);
+        double* xo = (double*)((step & 1) ? ctx->out[9].p : ctx->out[1].p);
+        if (step == 1) { CKC(ctx->out[8].reserve(sz_u)); CKC(ctx->out[9].reserve(sz_x)); uo = (double*)ctx->out[8].p; xo = (double*)ctx->out[9].p; }
+        rc = fsae_ltvmpc_dev(ctx, model, B, N, dt, d_tid, d_pid, (const double*)ctx->in[0].p, (const double*)ctx->in[1].p,
+                             xl, ul, uo, xo, (int32_t*)ctx->out[2].p, (double*)ctx->out[3].p, (double*)ctx->out[4].p,
+                             (int32_t*)ctx->out[5].p, nullptr, nullptr, st);
+        if (rc) { cleanup(); return rc; }
+        xl = xo;
+        ul = uo;
+    }
+    CKC(cudaMemcpyAsync(plant_final, plant.p, (size_t)B * 7 * 8, cudaMemcpyDeviceToHost, st));
+    CKC(cudaMemcpyAsync(steps, stepsb.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (n_hist) CKC(cudaMemcpyAsync(n_hist, nh.p, (size_t)B * n_sim * 8, cudaMemcpyDeviceToHost, st));
+    if (plant_hist) CKC(cudaMemcpyAsync(plant_hist, ph.p, (size_t)B * n_sim * 7 * 8, cudaMemcpyDeviceToHost, st));
+    if (exit_hist) CKC(cudaMemcpyAsync(exit_hist, eh.p, (size_t)B * n_sim * 4, cudaMemcpyDeviceToHost, st));
+    CKC(cudaStreamSynchronize(st));
+#undef CKC
+    cleanup();
     return FSAE_OK;
 }
 

@@ -169,6 +169,22 @@ int fsae_ltvmpc_sqp_host(fsae_ctx* ctx, int model, int B, int N_steps, double dt
                          double* u_opt, double* x_opt, int32_t* exitflag, double* fval,
                          double* slack_opt, int32_t* iters);
 
+/* ---- batch driver: main.m's closed loop (main.m:87-170) for B vehicles ----------------
+ * Per simulation step: projection of the plant state onto the track
+ * (cartesian_to_curvilinear.m / closest_point.m), x0 and speed-ramp reference (main.m:89-108),
+ * the fused LTV-MPC step linearised at the previous prediction (main.m:113-118), then the
+ * actuator PIDs and the Cartesian dynamic plant (main.m:146-160, pid_controller.m,
+ * integrate_cart_dyn.m).  A vehicle stops when s >= track length (main.m:97).
+ *   plant0 [7 x B]; x_opt0 [N_x*N x B], u_opt0 [N_u*N x B]: the initial guess of main.m:42-53.
+ * Outputs: plant_final [7 x B], steps [B] MPC steps taken; optional histories
+ * n_hist [n_sim x B] (lateral deviation, main.m:96), plant_hist [7 x n_sim x B] (x_history),
+ * exit_hist [n_sim x B]. */
+int fsae_closed_loop_host(fsae_ctx* ctx, int model, int B, int N_steps, double dt, int n_sim,
+                          double target_vel, const int32_t* track_id, const int32_t* param_id,
+                          const double* plant0, const double* x_opt0, const double* u_opt0,
+                          double* plant_final, int32_t* steps,
+                          double* n_hist, double* plant_hist, int32_t* exit_hist);
+
 /* ---- [x,fval,exitflag,iter,lambda,auxOutput] = qpOASES(H,g,A,lb,ub,lbA,ubA) ----------
  * (optimizers/matlab/qpOASES/qpOASES.m:22) for B independent dense QPs of one shape.
  * H [nV x nV x B] symmetric, A [nC x nV x B] column-major.  lambda [ (nV+nC) x B ] in
