@@ -236,13 +236,29 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
-    for _ in range(args.steps):
+    ee = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ee[0].record(ext)
+    for k in range(args.steps):
         step_e2e()
-    e1.record(ext)
+        ee[k + 1].record(ext)
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_ms = ee[0].elapsed_time(ee[-1])
+    e2e_step_ms = [ee[k].elapsed_time(ee[k + 1]) for k in range(args.steps)]
+
+    # ---------------- single-problem step latency (the control-loop view of the metric) -------
+    lat_us = []
+    if rank == 0:
+        one = dict(ptrs)
+        for _ in range(20):
+            mpc.ltvmpc_dev(fm.KINEMATIC, 1, N, DT, one, stream=mpc.stream)
+        torch.cuda.synchronize(dev)
+        for _ in range(200):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(ext)
+            mpc.ltvmpc_dev(fm.KINEMATIC, 1, N, DT, one, stream=mpc.stream)
+            a1.record(ext)
+            a1.synchronize()
+            lat_us.append(a0.elapsed_time(a1) * 1e3)
     h2d = sum(t.numel() * t.element_size() for t in h_in)
     d2h = sum(t.numel() * t.element_size() for t in h_out.values())
 
@@ -302,6 +318,13 @@ def run_ours(args, rank, local_rank, world):
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "api": "fsae_ltvmpc_host (C-ABI, pinned host buffers)"},
+            "latency": {"step_ms_p50": float(np.percentile(kern_ms, 50)), "step_ms_p99": float(np.percentile(kern_ms, 99)),
+                        "e2e_step_ms_p50": float(np.percentile(e2e_step_ms, 50)),
+                        "e2e_step_ms_p99": float(np.percentile(e2e_step_ms, 99)),
+                        "single_problem_us_p50": float(np.percentile(lat_us, 50)) if lat_us else None,
+                        "single_problem_us_p99": float(np.percentile(lat_us, 99)) if lat_us else None,
+                        "note": "step = one fused pass over batch_per_gpu problems (rank 0); single_problem = one "
+                                "MPC step of one vehicle, device-resident, 200 samples"},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,

@@ -90,7 +90,7 @@ extern "C" void fsae_default_params(int model, fsae_params* p) {
     p->ay_max = 5.0;
     p->slip_max = 0.1;
     p->ac_max = 9.163; p->al_max = 10.0;
-    p->max_iter = 1000;
+    p->max_iter = -1;             /* qpOASES: maxIter = -1 -> 5*(nV+nC) (qpOASES_options.m:40-41) */
     p->feas_tol = 1e-9;
     p->flat_eps = 1e-8;
 }

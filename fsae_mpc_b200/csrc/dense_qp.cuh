@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256, 1) dense_qp_kernel(DenseArgs a) {
         __syncthreads();
         Ops::initial_point(Q, m, ybuf, q, nCv, nV);
         const DenseProb<NVMAX> prob{S, A, lbA, ubA, nV, nC};
-        st = Ops::solve(prob, Q, m, lam, q, ybuf, nV, a.feas_tol, a.max_iter);
+        st = Ops::solve(prob, Q, m, lam, q, ybuf, nV, a.feas_tol, a.max_iter > 0 ? a.max_iter : 5 * (nV + nC));
     }
     __syncthreads();
     // outputs

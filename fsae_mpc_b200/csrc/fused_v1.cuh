@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
 
     // ---------------------------------------------------------------- Goldfarb-Idnani, K-form
     const double tol = P.feas_tol;
-    const int max_iter = P.max_iter;
+    const int max_iter = P.max_iter > 0 ? P.max_iter : 5 * (nV + C::n_ref_rows(N));
     unsigned long long n_add = 0, n_drop = 0;
     while (true) {
         // P1: most violated inactive constraint side

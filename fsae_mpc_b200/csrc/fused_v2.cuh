@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     __syncthreads();
     Ops::initial_point(Q, m, ybuf, q, nU, nV);             // x_u = -J J' g, slacks at 0
     const MpcProb<Model, N, NW_> prob{S, P, dt};
-    const GiStats st = Ops::solve(prob, Q, m, lam, q, ybuf, nV, P.feas_tol, P.max_iter);
+    const GiStats st = Ops::solve(prob, Q, m, lam, q, ybuf, nV, P.feas_tol, P.max_iter > 0 ? P.max_iter : 5 * (nV + C::n_ref_rows(N)));
     const int iters = st.iters, exitflag = st.exitflag, n_add = st.n_add, n_drop = st.n_drop, n_refresh = st.n_refresh;
 
     // ---------------------------------------------------------------- outputs

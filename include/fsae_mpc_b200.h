@@ -75,7 +75,8 @@ typedef struct fsae_params {
     double ac_max, al_max;          /* 9.163, 10.0 */
     /* solver */
     int lin_scheme;                 /* FSAE_LIN_*; reference: RK2 kinematic, RK4 dynamic */
-    int max_iter;                   /* active-set iteration cap -> exitflag 1 */
+    int max_iter;                   /* active-set iteration cap -> exitflag 1; <= 0: qpOASES's
+                                       heuristic 5*(nV+nC) (qpOASES_options.m:40-41) */
     double feas_tol;                /* constraint violation tolerance (absolute) */
     double flat_eps;                /* curvature given to zero-Hessian slack variables when
                                        one of their bounds leaves the working set */
