@@ -772,3 +772,16 @@ extern "C" int fsae_debug_set_kernel_version(fsae_ctx* ctx, int v) {
     ctx->kernel_version = v;
     return old;
 }
+
+#ifdef FSAE_PROFILE
+extern "C" int fsae_profile_read(fsae_ctx* ctx, uint64_t* out16, int reset) {
+    if (!ctx || !out16) return FSAE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    unsigned long long h[16];
+    CK(cudaMemcpyFromSymbol(h, fsae::g_phase_cycles, sizeof(h)));
+    for (int i = 0; i < 16; ++i) out16[i] = h[i];
+    if (reset) { memset(h, 0, sizeof(h)); CK(cudaMemcpyToSymbol(fsae::g_phase_cycles, h, sizeof(h))); }
+    return FSAE_OK;
+}
+#endif

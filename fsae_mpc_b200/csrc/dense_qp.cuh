@@ -63,10 +63,11 @@ struct DenseProb {
             if (vup < best) { best = vup; best_i = slot * 2 + 1; }
         }
     }
-    __device__ __forceinline__ double normal_entry(int pslot, int pside, int i) const {
-        const double sg = pside < 0 ? 1.0 : -1.0;
-        if (pslot < nV) return (i == pslot) ? sg : 0.0;
-        return sg * A[(size_t)S.perm[i] * nC + (pslot - nV)];
+    struct Prep { int pslot; double sg; };
+    __device__ __forceinline__ Prep normal_prepare(int pslot, int pside) const { return {pslot, pside < 0 ? 1.0 : -1.0}; }
+    __device__ __forceinline__ double normal_entry(const Prep& p, int i) const {
+        if (p.pslot < nV) return (i == p.pslot) ? p.sg : 0.0;
+        return p.sg * A[(size_t)S.perm[i] * nC + (p.pslot - nV)];
     }
     __device__ __forceinline__ double norm2(int) const { return 1.0; }
     __device__ __forceinline__ bool is_unit(int pslot) const { return pslot < nV; }

@@ -146,28 +146,54 @@ struct MpcProb {
         }
     }
 
-    // entry i of the normal of (slot, side) in  n'x >= b  form
-    __device__ __forceinline__ double normal_entry(int pslot, int pside, int i) const {
+    // Normal of (slot, side) in  n'x >= b  form.  Everything that depends only on the slot is
+    // computed once, warp-uniformly (no divergence); the per-entry part is one shared-memory
+    // load and selects.
+    struct Prep {
+        int pslot, k;            // k = horizon step of a row slot, -1 for a variable bound
+        double sg;
+        double creal[C::NCR];    // coefficients of the packed B_bar rows
+        double cctl[D::NU];      // dt * (integrator-state coefficients) per control column
+        double cu[D::NU];        // direct control coefficients at step k
+        int slack;               // absolute index of the slack entry, -1 if none
+    };
+    __device__ __forceinline__ Prep normal_prepare(int pslot, int pside) const {
         constexpr int NU = D::NU, nU = D::nU, nV = D::nV;
-        const double sg = pside < 0 ? 1.0 : -1.0;
-        if (pslot < nV) return (i == pslot) ? sg : 0.0;
-        const int rr = pslot - nV, r = rr / N, k = rr - r * N;
-        if (i >= nU) {
+        Prep p;
+        p.pslot = pslot;
+        p.sg = pside < 0 ? 1.0 : -1.0;
+        p.k = -1;
+        p.slack = -1;
+#pragma unroll
+        for (int c = 0; c < C::NCR; ++c) p.creal[c] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) { p.cctl[c] = 0.0; p.cu[c] = 0.0; }
+        if (pslot >= nV) {
+            const int rr = pslot - nV, r = rr / N, k = rr - r * N;
+            const double* pc = S.pc + k * C::NPC;
+            p.k = k;
             const int sl = C::row_slack(r);
-            return (sl >= 0 && i == nU + sl) ? 1.0 : 0.0;
+            p.slack = sl >= 0 ? nU + sl : -1;
+#pragma unroll
+            for (int c = 0; c < C::NCR; ++c) p.creal[c] = p.sg * C::row_coef(r, c, pc, S.cg);
+#pragma unroll
+            for (int c = 0; c < C::NINT; ++c) p.cctl[C::int_ucol(c)] += p.sg * dt * C::row_coef(r, C::NCR + c, pc, S.cg);
+#pragma unroll
+            for (int c = 0; c < NU; ++c) p.cu[c] = p.sg * C::row_ucoef(r, c, pc, S.cg);
         }
+        return p;
+    }
+    __device__ __forceinline__ double normal_entry(const Prep& p, int i) const {
+        constexpr int NU = D::NU, nU = D::nU;
+        if (p.k < 0) return (i == p.pslot) ? p.sg : 0.0;               // uniform branch
         const int step = i / NU, uc = i - step * NU;
-        if (step > k) return 0.0;
-        const double* pc = S.pc + k * C::NPC;
-        double acc = 0.0;
+        const bool in = (i < nU) & (step <= p.k);
+        double acc = (uc == 0) ? p.cctl[0] : p.cctl[NU - 1];
+        acc += (step == p.k) ? ((uc == 0) ? p.cu[0] : p.cu[NU - 1]) : 0.0;
+        const int idx = in ? D::pk(p.k, i) : 0;
 #pragma unroll
-        for (int c = 0; c < C::NCR; ++c)
-            acc += C::row_coef(r, c, pc, S.cg) * S.Bf[C::cons_real(c) * D::NPK + D::pk(k, i)];
-#pragma unroll
-        for (int c = 0; c < C::NINT; ++c)
-            if (C::int_ucol(c) == uc) acc += C::row_coef(r, C::NCR + c, pc, S.cg) * dt;
-        if (step == k) acc += C::row_ucoef(r, uc, pc, S.cg);
-        return sg * acc;
+        for (int c = 0; c < C::NCR; ++c) acc = fma(p.creal[c], S.Bf[C::cons_real(c) * D::NPK + idx], acc);
+        return in ? acc : ((i == p.slack) ? 1.0 : 0.0);
     }
 
     __device__ __forceinline__ double norm2(int pslot) const {

@@ -21,6 +21,19 @@
 
 namespace fsae {
 
+// Phase timers for kernel tuning (scripts/phase_profile.py builds a separate .so with
+// -DFSAE_PROFILE; the product build compiles them out).
+#ifdef FSAE_PROFILE
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_DECL long long ph_t_ = clock64(); unsigned long long ph_acc_[12] = {0}
+#define PHASE(i) do { const long long n_ = clock64(); ph_acc_[i] += (unsigned long long)(n_ - ph_t_); ph_t_ = n_; } while (0)
+#define PHASE_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 12; ++i_) atomicAdd(&g_phase_cycles[i_], ph_acc_[i_]); } while (0)
+#else
+#define PHASE_DECL
+#define PHASE(i)
+#define PHASE_FLUSH
+#endif
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -330,11 +343,14 @@ struct GiOps {
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row0 = warp * RPW;
         GiStats st = {0, GI_EXIT_SOLVED, 0, 0, 0};
         int rbuf = 0;
+        PHASE_DECL;
         while (true) {
             // P1: most violated inactive constraint side (policy evaluates its slots)
             double best = 0.0;
             int best_i = 0x7fffffff;
+            PHASE(0);
             prob.search(best, best_i);
+            PHASE(1);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const double ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -352,6 +368,7 @@ struct GiOps {
                 if (ov < viol || (ov == viol && oi < pcode)) { viol = ov; pcode = oi; }
             }
             rbuf ^= 1;
+            PHASE(2);
 
             if (!(viol < -tol)) {
                 // the refresh repairs what chains of partial steps leave behind; a run of pure
@@ -379,12 +396,16 @@ struct GiOps {
             double sp = viol;                                   // n'x - b  (< 0)
             double lam_p = 0.0;
             // P2: this warp's entries of the normal
-            if (lane < RPW) {
-                const int i = row0 + lane;
-                S.nvec[i] = (i < nV) ? prob.normal_entry(pslot, pside, i) : 0.0;
+            {
+                const auto prep = prob.normal_prepare(pslot, pside);      // warp-uniform part
+                if (lane < RPW) {
+                    const int i = row0 + lane;
+                    S.nvec[i] = (i < nV) ? prob.normal_entry(prep, i) : 0.0;
+                }
             }
             __syncwarp();
             const double nn = prob.norm2(pslot);
+            PHASE(3);
 
             bool failed = false;
             while (true) {
@@ -410,17 +431,21 @@ struct GiOps {
                 } else {
                     matvec_T(S, m, ybuf, S.nvec, 0.0, y, dummy);
                 }
+                PHASE(4);
                 // P4 (every warp, redundantly): step lengths
                 double d2 = 0.0, t1 = INFINITY;
                 int l = -1;
 #pragma unroll
-                for (int s = 0; s < CS; ++s) {
+                for (int s = 0; s < CS; ++s) {      // branch-free: every lane does the same work
                     const int j = lane + 32 * s;
-                    if (j >= q && j < nV) d2 += y[s] * y[s];
-                    else if (j < q && y[s] > 1e-13) {
-                        const double tj = lam[s] * __drcp_rn(y[s]);
-                        if (tj < t1) { t1 = tj; l = j; }
-                    }
+                    const double yy = y[s];
+                    const bool isJ = (j >= q) & (j < nV);
+                    const bool cand = (j < q) & (yy > 1e-13);
+                    d2 = fma(isJ ? yy : 0.0, yy, d2);
+                    const double tj = cand ? lam[s] * __drcp_rn(cand ? yy : 1.0) : INFINITY;
+                    const bool better = tj < t1;
+                    t1 = better ? tj : t1;
+                    l = better ? j : l;
                 }
                 d2 = warp_sum_d(d2);
                 {
@@ -438,6 +463,7 @@ struct GiOps {
                 const bool full = (t2 <= t1);
                 const bool primal = !isinf(t2);
                 const double t = full ? t2 : t1;
+                PHASE(5);
                 // P5: z = J2 y2, x += t z
                 if (primal) {
                     matvec_N(S, m, y, q, nV);
@@ -463,6 +489,7 @@ struct GiOps {
                     if (j < q) lam[s] -= t * y[s];
                 }
                 lam_p += t;
+                PHASE(6);
                 if (full) {
                     // P6a: add p.  K1 <- K1 - k r', J2 <- J2 (I - beta v v'), column q <- k = z/d2
                     const int qs = q >> 5, ql = q & 31;
@@ -509,6 +536,7 @@ struct GiOps {
                     ++q;
                     ++st.n_add;
                     __syncwarp();
+                    PHASE(7);
                     break;
                 }
                 // P6b: drop active constraint l (column l of K1)
@@ -573,11 +601,13 @@ struct GiOps {
                     }
                     --q;
                     ++st.n_drop;
+                    PHASE(8);
                 }
             }
             if (failed) break;
         }
         __syncthreads();
+        PHASE_FLUSH;
         return st;
     }
 

@@ -1,0 +1,37 @@
+"""Per-phase cycle breakdown of the dual active-set loop (warp 0's clock64 deltas), from a
+separate -DFSAE_PROFILE build (the product .so is not touched).
+    python scripts/phase_profile.py [B]"""
+import ctypes as C, os, subprocess, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+prof_so = os.path.join(ROOT, "build", "libfsae_prof.so")
+if not os.path.exists(prof_so):
+    os.makedirs(os.path.dirname(prof_so), exist_ok=True)
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DFSAE_PROFILE", "-shared",
+                    "-Xcompiler", "-fPIC", "-o", prof_so, os.path.join(ROOT, "fsae_mpc_b200", "csrc", "capi.cu")], check=True)
+from fsae_mpc_b200 import _lib
+_lib.LIB_PATH = prof_so
+import fsae_mpc_b200 as fm
+from fsae_mpc_b200 import workload as wl
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 296
+mpc = fm.FsaeMpc(0)
+for tid, (n, t) in enumerate(wl.load_tracks().items()):
+    mpc.set_track(tid, t[0], t[1], t[2])
+lib = mpc._lib
+lib.fsae_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
+x0, xr, xl, ul = wl.perturbed_batch("kinematic", "fsg2019", B, 0)
+out = (C.c_uint64 * 16)()
+mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, 0.05, xl, ul)
+lib.fsae_profile_read(mpc._ctx, out, 1)
+mpc.counters(reset=True)
+r = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, 0.05, xl, ul)
+lib.fsae_profile_read(mpc._ctx, out, 1)
+adds, drops, refr = mpc.counters()
+names = ["loop/refresh overhead", "P1 search (policy)", "P1 argmin+barrier", "P2 normal", "P3 y=M'n (+barrier)", "P4 step lengths",
+         "P5 z=J2y2, x update (+barrier)", "P6a add update", "P6b drop"]
+tot = sum(out[i] for i in range(9))
+it = r.iters.sum()
+print(f"B={B}: iterations {it} (adds {adds}, drops {drops}), cycles in loop per QP {tot/B:.0f}, per iteration {tot/it:.0f}")
+for i, n in enumerate(names):
+    print(f"  {n:34s} {out[i]/it:8.0f} cyc/iter  {100*out[i]/tot:5.1f}%")
