@@ -407,10 +407,10 @@ static int launch_fused_long(fsae_ctx* ctx, BatchArgs a, cudaStream_t st) {
     return FSAE_OK;
 }
 
-template <class Model, int N, int MINB, int NW = 8>
+template <class Model, int N, int MINB, int NW = 8, int KB = 1>
 static int launch_fused_v2(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
-    using S_t = SmemV2<Model, N, NW>;
-    auto kern = ltvmpc_fused_v2_kernel<Model, N, MINB, NW>;
+    using S_t = SmemV2<Model, N, NW, KB>;
+    auto kern = ltvmpc_fused_v2_kernel<Model, N, MINB, NW, KB>;
     static bool configured[64] = {false};
     if (!configured[ctx->device & 63]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S_t)));
@@ -448,7 +448,20 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
     int rc = FSAE_ERR_UNSUPPORTED;
     if (model == FSAE_MODEL_KINEMATIC) {
         const bool v1 = ctx->kernel_version == 1;
-        if (N == 40) rc = v1 ? launch_fused_v1<KinModel, 40, 256>(ctx, a, st) : launch_fused_v2<KinModel, 40, 2>(ctx, a, st);
+        const int kv = ctx->kernel_version;      // 2x: block size x (tuning/cross-check switch)
+        if (N == 40) rc = v1 ? launch_fused_v1<KinModel, 40, 256>(ctx, a, st)
+                     : kv == 21 ? launch_fused_v2<KinModel, 40, 2, 8, 1>(ctx, a, st)
+                     : kv == 22 ? launch_fused_v2<KinModel, 40, 2, 8, 2>(ctx, a, st)
+                     : kv == 23 ? launch_fused_v2<KinModel, 40, 2, 8, 3>(ctx, a, st)
+                     : kv == 25 ? launch_fused_v2<KinModel, 40, 2, 5, 1>(ctx, a, st)
+                     : kv == 29 ? launch_fused_v2<KinModel, 40, 2, 4, 1>(ctx, a, st)
+                     : kv == 30 ? launch_fused_v2<KinModel, 40, 2, 4, 2>(ctx, a, st)
+                     : kv == 31 ? launch_fused_v2<KinModel, 40, 2, 4, 3>(ctx, a, st)
+                     : kv == 32 ? launch_fused_v2<KinModel, 40, 2, 4, 4>(ctx, a, st)
+                     : kv == 26 ? launch_fused_v2<KinModel, 40, 2, 6, 1>(ctx, a, st)
+                     : kv == 27 ? launch_fused_v2<KinModel, 40, 2, 6, 2>(ctx, a, st)
+                     : kv == 28 ? launch_fused_v2<KinModel, 40, 2, 6, 3>(ctx, a, st)
+                     : launch_fused_v2<KinModel, 40, 2, 6, 1>(ctx, a, st);
         else if (N == 20) rc = v1 ? launch_fused_v1<KinModel, 20, 256>(ctx, a, st) : launch_fused_v2<KinModel, 20, 2>(ctx, a, st);
         else if (N == 80) rc = launch_fused_long<KinModel, 80>(ctx, a, st);
         else ctx->err = "kinematic fused step: horizon must be 20, 40 or 80";
@@ -767,7 +780,7 @@ extern "C" int fsae_probe_fp64_tflops(fsae_ctx* ctx, double* tflops) {
 
 // select the fused kernel variant (tests cross-check v1 against v2); returns the previous one
 extern "C" int fsae_debug_set_kernel_version(fsae_ctx* ctx, int v) {
-    if (!ctx || (v != 1 && v != 2)) return FSAE_ERR_ARG;
+    if (!ctx || (v != 1 && v != 2 && (v < 21 || v > 39))) return FSAE_ERR_ARG;
     const int old = ctx->kernel_version;
     ctx->kernel_version = v;
     return old;
@@ -782,6 +795,16 @@ extern "C" int fsae_profile_read(fsae_ctx* ctx, uint64_t* out16, int reset) {
     CK(cudaMemcpyFromSymbol(h, fsae::g_phase_cycles, sizeof(h)));
     for (int i = 0; i < 16; ++i) out16[i] = h[i];
     if (reset) { memset(h, 0, sizeof(h)); CK(cudaMemcpyToSymbol(fsae::g_phase_cycles, h, sizeof(h))); }
+    return FSAE_OK;
+}
+extern "C" int fsae_profile_read_stages(fsae_ctx* ctx, uint64_t* out16, int reset) {
+    if (!ctx || !out16) return FSAE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    unsigned long long h[16];
+    CK(cudaMemcpyFromSymbol(h, fsae::g_stage_cycles, sizeof(h)));
+    for (int i = 0; i < 16; ++i) out16[i] = h[i];
+    if (reset) { memset(h, 0, sizeof(h)); CK(cudaMemcpyToSymbol(fsae::g_stage_cycles, h, sizeof(h))); }
     return FSAE_OK;
 }
 #endif

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256, 1) dense_qp_kernel(DenseArgs a) {
     const double* ubA = a.ubA + (size_t)b * nC;
 
     for (int i = tid; i < nV + nC; i += NT) Q.status[i] = 0;
-    for (int i = tid; i < G::RP; i += NT) { Q.x[i] = 0.0; Q.g[i] = 0.0; Q.rowv[i] = 0.0; Q.nvec[i] = 0.0; Q.zrow[i] = 0.0; Q.colk[0][i] = 0.0; Q.colk[1][i] = 0.0; }
+    for (int i = tid; i < G::RP; i += NT) { Q.x[i] = 0.0; Q.g[i] = 0.0; Q.rowv[i] = 0.0; Q.nvec[0][i] = 0.0; Q.zrow[i] = 0.0; Q.colk[0][i] = 0.0; Q.colk[1][i] = 0.0; }
     if (tid == 0) {
         // curved variables first (caller's order), zero-curvature ones last
         int nc = 0, nf = 0;

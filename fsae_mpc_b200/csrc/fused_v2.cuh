@@ -22,14 +22,14 @@
 
 namespace fsae {
 
-template <class Model, int N, int NW_ = 8>
-using CfgV2 = GiCfg<Dims<Model, N>::nV, NW_>;
+template <class Model, int N, int NW_ = 8, int KB_ = 1>
+using CfgV2 = GiCfg<Dims<Model, N>::nV, NW_, KB_>;
 
-template <class Model, int N, int NW_ = 8>
+template <class Model, int N, int NW_ = 8, int KB_ = 1>
 struct SmemV2 {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
-    using G = CfgV2<Model, N, NW_>;
+    using G = CfgV2<Model, N, NW_, KB_>;
     alignas(16) double Bf[C::NREAL * D::NPK];   // packed B_bar rows of the "real" states (kept to the end)
     GiSm<G, D::NSLOT> gi;                       // x, g, packed H, working set, core scratch
     double Ad[N * C::NREAL * D::NX];
@@ -43,8 +43,13 @@ struct SmemV2 {
     double cg[C::NCG];
     double rlo[D::NROWS], rup[D::NROWS];
     double rn2[D::NROWS];              // squared norm of each row's normal (linear-dependence test)
+    static constexpr bool ROWNORMS = D::NROWS <= 256;  // larger row sets use 1 as the scale
+    static constexpr int NGR = C::NCR * (C::NCR + 1) / 2;
+    double gram[ROWNORMS ? N * NGR : 1];            // per step: Gram matrix of the constraint B_bar rows
+    double csum[ROWNORMS ? N * C::NCR * D::NU : 1]; // per step: their sums over each control's columns
     double dd[N * D::NX];
     double scal[8];                    // 0 cost const
+    alignas(8) fsae_params prm;        // this problem's parameter set (copied once: no global loads in the loops)
     alignas(8) unsigned long long mbar; // mbarrier of the input staging
 };
 
@@ -72,12 +77,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
 // Problem policy of the core for the LTV-MPC QPs: slots [0, nV) are the variable bounds
 // (ltvmpc_*_curvilinear.m:28-29), slots nV + r*N + k the constraint row r at horizon step k
 // (cons.cuh).  Nothing dense is ever formed.
-template <class Model, int N, int NW_>
+template <class Model, int N, int NW_, int KB_>
 struct MpcProb {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
-    using G = CfgV2<Model, N, NW_>;
-    SmemV2<Model, N, NW_>& S;
+    using G = CfgV2<Model, N, NW_, KB_>;
+    SmemV2<Model, N, NW_, KB_>& S;
     const fsae_params& P;
     double dt;
 
@@ -87,12 +92,11 @@ struct MpcProb {
     __device__ __forceinline__ void search(double& best, int& best_i) const {
         constexpr int NU = D::NU, nU = D::nU, nV = D::nV, NT = G::NT;
         constexpr int ROWT = ((4 * N + 31) / 32) * 32;      // row threads, rounded up to whole warps
-        static_assert(ROWT + nV <= NT, "P1 thread map needs ceil32(4N) + nV <= threads per CTA");
         static_assert(NU == 2, "paired (double2) row loads assume two controls per step");
-        const int tid = threadIdx.x, warp = tid >> 5;
+        const int tid = threadIdx.x;
         const double* x = S.gi.x;
-        if (warp < (4 * N + 31) / 32) {
-            const int k = tid >> 2, part = tid & 3;
+        for (int rt = tid; rt < ROWT; rt += NT) {            // warp-uniform trip count
+            const int k = rt >> 2, part = rt & 3;
             const bool valid = k < N;
             double acc[C::NXS];
 #pragma unroll
@@ -133,9 +137,11 @@ struct MpcProb {
                     if (vup < best) { best = vup; best_i = slot * 2 + 1; }
                 }
             }
-        } else {
-            const int slot = tid - ROWT;
-            if (slot >= 0 && slot < nV && S.gi.status[slot] == 0) {
+        }
+        // variable bounds: dealt round-robin starting at the first thread after the row threads
+        // (with 256 threads: one slot per thread of the three bound warps, as before)
+        for (int slot = (tid + NT - ROWT % NT) % NT; slot < nV; slot += NT) {
+            if (S.gi.status[slot] == 0) {
                 const double xv = x[slot];
                 const double lb = (slot < nU) ? P.u_lb[slot % NU] : 0.0;
                 const double ub = (slot < nU) ? P.u_ub[slot % NU] : INFINITY;
@@ -202,12 +208,12 @@ struct MpcProb {
     __device__ __forceinline__ bool is_unit(int pslot) const { return pslot < D::nV; }
 };
 
-template <class Model, int N, int MINB, int NW_ = 8>
+template <class Model, int N, int MINB, int NW_ = 8, int KB_ = 1>
 __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchArgs a) {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
-    using G = CfgV2<Model, N, NW_>;
-    using S_t = SmemV2<Model, N, NW_>;
+    using G = CfgV2<Model, N, NW_, KB_>;
+    using S_t = SmemV2<Model, N, NW_, KB_>;
     constexpr int NX = D::NX, NU = D::NU, NS = D::NS, nU = D::nU, nV = D::nV;
     constexpr int NT = G::NT, NW = G::NW, RPW = G::RPW, CS = G::CS, RP = G::RP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -215,11 +221,16 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x;
     if (b >= a.B) return;
-    const fsae_params& P = a.params[a.param_id ? a.param_id[b] : 0];
+    const fsae_params& Pg = a.params[a.param_id ? a.param_id[b] : 0];
+    static_assert(sizeof(fsae_params) % 8 == 0, "parameter set is copied as 64-bit words");
+    for (int i = tid; i < (int)(sizeof(fsae_params) / 8); i += 32 * NW_)
+        reinterpret_cast<unsigned long long*>(&S.prm)[i] = reinterpret_cast<const unsigned long long*>(&Pg)[i];
+    const fsae_params& P = S.prm;      // visible after the barrier that ends the load stage
     const DevTrack tr = a.tracks[a.track_id ? a.track_id[b] : 0];
     const double dt = a.dt;
     const int row0 = warp * RPW;            // first row of this warp
 
+    STAGE_DECL;
     // ---------------------------------------------------------------- load (TMA bulk copies)
     // x_lin, u_lin, x_ref of one problem are contiguous records: one elected thread issues
     // three cp.async.bulk copies that complete on an mbarrier while the other threads clear
@@ -242,7 +253,8 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             }
         }
         for (int i = tid; i < D::NSLOT; i += NT) S.gi.status[i] = 0;
-        for (int i = tid; i < RP; i += NT) { S.gi.x[i] = 0.0; S.gi.g[i] = 0.0; S.gi.rowv[i] = 0.0; S.gi.nvec[i] = 0.0; S.gi.zrow[i] = 0.0; S.gi.colk[0][i] = 0.0; S.gi.colk[1][i] = 0.0; }
+        for (int i = tid; i < KB_ * RP; i += NT) (&S.gi.nvec[0][0])[i] = 0.0;
+        for (int i = tid; i < RP; i += NT) { S.gi.x[i] = 0.0; S.gi.g[i] = 0.0; S.gi.rowv[i] = 0.0; S.gi.zrow[i] = 0.0; S.gi.colk[0][i] = 0.0; S.gi.colk[1][i] = 0.0; }
         if (aligned) {
             mbar_wait(&S.mbar, 0);
         } else {
@@ -252,6 +264,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     }
     __syncthreads();
 
+    STAGE(0);
     // ---------------------------------------------------------------- linearise + discretise
     if (tid < N) {
         const int k = tid;
@@ -276,6 +289,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     }
     __syncthreads();
 
+    STAGE(1);
     // ---------------------------------------------------------------- free response + B_bar chains
     if (warp == NW - 1) {
         if (lane == 0) {
@@ -328,10 +342,41 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     }
     __syncthreads();
 
+    STAGE(2);
     // ---------------------------------------------------------------- g, bounds, row norms, cost const
     {
         double* e = S.dd;      // tracking error overwrites dd (dead after the free response)
         for (int i = tid; i < NX * N; i += NT) e[i] = S.xf[i] - S.xr[i];
+        if (S_t::ROWNORMS) {
+            // per-step Gram matrix / column sums of the B_bar rows the constraints touch: the squared
+            // norm of every row normal then has a closed form (below)
+            for (int k = NT - 1 - tid; k < N; k += NT) {      // the last threads: the first ones have the longest g sums
+                double G[S_t::NGR], Sm[C::NCR * NU];
+#pragma unroll
+                for (int i = 0; i < S_t::NGR; ++i) G[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < C::NCR * NU; ++i) Sm[i] = 0.0;
+                for (int j = 0; j < NU * (k + 1); j += NU) {
+#pragma unroll
+                    for (int u = 0; u < NU; ++u) {
+                        double bc[C::NCR];
+#pragma unroll
+                        for (int c = 0; c < C::NCR; ++c) bc[c] = S.Bf[C::cons_real(c) * D::NPK + D::pk(k, j + u)];
+                        int gi = 0;
+#pragma unroll
+                        for (int c = 0; c < C::NCR; ++c) {
+                            Sm[c * NU + u] += bc[c];
+#pragma unroll
+                            for (int c2 = 0; c2 <= c; ++c2, ++gi) G[gi] = fma(bc[c], bc[c2], G[gi]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < S_t::NGR; ++i) S.gram[k * S_t::NGR + i] = G[i];
+#pragma unroll
+                for (int i = 0; i < C::NCR * NU; ++i) S.csum[k * C::NCR * NU + i] = Sm[i];
+            }
+        }
         __syncthreads();
         for (int j = tid; j < nV; j += NT) {
             double acc = 0.0;
@@ -376,27 +421,42 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             S.rlo[t] = lo;
             S.rup[t] = up;
             // squared norm of the row normal (u part + slack entry); only a scale for the
-            // linear-dependence threshold, so large row sets use 1
-            const double* pc = S.pc + k * C::NPC;
+            // linear-dependence threshold.  With v_j = sum_c a_c B_c[k][j] + b_u(j) + [step(j) = k] cu_u(j):
+            //   |v|^2 = a'G a + 2 sum_u b_u (a'S_u) + (k+1) sum_u b_u^2 + sum_u cu_u (2 (a'B[.,2k+u] + b_u) + cu_u)
             double n2 = 1.0;
-            if (D::NROWS <= 256) {
+            if (S_t::ROWNORMS) {
+                const double* pc = S.pc + k * C::NPC;
+                double ac[C::NCR], bu[NU];
+#pragma unroll
+                for (int c = 0; c < C::NCR; ++c) ac[c] = C::row_coef(r, c, pc, S.cg);
+#pragma unroll
+                for (int u = 0; u < NU; ++u) bu[u] = 0.0;
+#pragma unroll
+                for (int c = 0; c < C::NINT; ++c) bu[C::int_ucol(c)] += C::row_coef(r, C::NCR + c, pc, S.cg) * dt;
                 n2 = (C::row_slack(r) >= 0) ? 1.0 : 0.0;
-                for (int j = 0; j < NU * (k + 1); ++j) {
-                    const int step = j / NU, uc = j - step * NU;
-                    double v = 0.0;
+                int gi = 0;
 #pragma unroll
-                    for (int c = 0; c < C::NCR; ++c) v += C::row_coef(r, c, pc, S.cg) * S.Bf[C::cons_real(c) * D::NPK + D::pk(k, j)];
+                for (int c = 0; c < C::NCR; ++c) {
 #pragma unroll
-                    for (int c = 0; c < C::NINT; ++c)
-                        if (C::int_ucol(c) == uc) v += C::row_coef(r, C::NCR + c, pc, S.cg) * dt;
-                    if (step == k) v += C::row_ucoef(r, uc, pc, S.cg);
-                    n2 += v * v;
+                    for (int c2 = 0; c2 <= c; ++c2, ++gi) n2 += (c2 == c ? 1.0 : 2.0) * ac[c] * ac[c2] * S.gram[k * S_t::NGR + gi];
+                }
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    double aS = 0.0, aB = 0.0;
+#pragma unroll
+                    for (int c = 0; c < C::NCR; ++c) {
+                        aS += ac[c] * S.csum[(k * C::NCR + c) * NU + u];
+                        aB += ac[c] * S.Bf[C::cons_real(c) * D::NPK + D::pk(k, NU * k + u)];
+                    }
+                    const double cu = C::row_ucoef(r, u, pc, S.cg);
+                    n2 += bu[u] * (2.0 * aS + (double)(k + 1) * bu[u]) + cu * (2.0 * (aB + bu[u]) + cu);
                 }
             }
             S.rn2[t] = n2;
         }
     }
 
+    STAGE(3);
     // ---------------------------------------------------------------- H in register tiles
     // generate_qp.m:29  H = 2 (B' Qbar B + Rbar) accumulated as a sum of rank-1 terms
     // q_{k,c} b_{k,c} b_{k,c}' over the rows (k, c) of B_bar, directly into the tile layout.
@@ -482,6 +542,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
         for (int t = tid; t < nV; t += NT) gg[t] = S.gi.g[t];
     }
 
+    STAGE(4);
     // ---------------------------------------------------------------- factor, lay out, solve
     using Ops = GiOps<G, GiSm<G, D::NSLOT>>;
     GiSm<G, D::NSLOT>& Q = S.gi;
@@ -493,11 +554,14 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
         Q.status[nU + tid] = -1;                           // multiplier R_soft (dual feasible start)
     }
     __syncthreads();
+    STAGE(5);
     Ops::initial_point(Q, m, ybuf, q, nU, nV);             // x_u = -J J' g, slacks at 0
-    const MpcProb<Model, N, NW_> prob{S, P, dt};
+    STAGE(6);
+    const MpcProb<Model, N, NW_, KB_> prob{S, P, dt};
     const GiStats st = Ops::solve(prob, Q, m, lam, q, ybuf, nV, P.feas_tol, P.max_iter > 0 ? P.max_iter : 5 * (nV + C::n_ref_rows(N)));
     const int iters = st.iters, exitflag = st.exitflag, n_add = st.n_add, n_drop = st.n_drop, n_refresh = st.n_refresh;
 
+    STAGE(7);
     // ---------------------------------------------------------------- outputs
     // fval = 1/2 x'Hx + g'x + const (ltvmpc_*_curvilinear.m:60); H without the flat_eps entries
     {
@@ -559,6 +623,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             }
         }
     }
+    STAGE(8);
 }
 
 }  // namespace fsae

@@ -25,12 +25,20 @@ namespace fsae {
 // -DFSAE_PROFILE; the product build compiles them out).
 #ifdef FSAE_PROFILE
 __device__ unsigned long long g_phase_cycles[16];
-#define PHASE_DECL long long ph_t_ = clock64(); unsigned long long ph_acc_[12] = {0}
+#define PHASE_DECL long long ph_t_ = clock64(); unsigned long long ph_acc_[16] = {0}
 #define PHASE(i) do { const long long n_ = clock64(); ph_acc_[i] += (unsigned long long)(n_ - ph_t_); ph_t_ = n_; } while (0)
-#define PHASE_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 12; ++i_) atomicAdd(&g_phase_cycles[i_], ph_acc_[i_]); } while (0)
+#define PHASE_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 16; ++i_) atomicAdd(&g_phase_cycles[i_], ph_acc_[i_]); } while (0)
+#define PHASE_COUNT(i) do { ++ph_acc_[i]; } while (0)
+// stage timers of the enclosing kernel (tid 0): g_stage_cycles[i] += cycles since the previous mark
+__device__ unsigned long long g_stage_cycles[16];
+#define STAGE_DECL long long sg_t_ = clock64()
+#define STAGE(i) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_stage_cycles[i], (unsigned long long)(n_ - sg_t_)); sg_t_ = n_; } } while (0)
 #else
+#define STAGE_DECL
+#define STAGE(i)
 #define PHASE_DECL
 #define PHASE(i)
+#define PHASE_COUNT(i)
 #define PHASE_FLUSH
 #endif
 
@@ -40,89 +48,63 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-// ---- in-warp reduce-scatter of RH values: afterwards lane l (and its RH-group partners) hold
-// the warp-wide sum of entry (l >> 1) [RH = 16] or (l >> 2) [RH = 8].
+
+// ---- exact warp arg-min of doubles with two 32-bit REDUX ops -------------------------------
+// dkey maps a double to an unsigned 64-bit key with the same order (negative < positive).
+__device__ __forceinline__ unsigned long long dkey(double v) {
+    const long long b = __double_as_longlong(v);
+    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    const long long b = (k & 0x8000000000000000ull) ? (long long)(k & 0x7fffffffffffffffull) : (long long)~k;
+    return __longlong_as_double(b);
+}
+constexpr unsigned long long DKEY_NONE = 0x8000000000000000ull;      // dkey(+0.0): "no candidate"
+// lowest lane holding the minimum key; kmin = that key (identical in every lane)
+__device__ __forceinline__ int warp_argmin_key(unsigned long long key, unsigned long long& kmin) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, (hi == mh) ? lo : 0xffffffffu);
+    const unsigned who = __ballot_sync(0xffffffffu, hi == mh && lo == ml);
+    kmin = ((unsigned long long)mh << 32) | ml;
+    return __ffs(who) - 1;
+}
+
+// ---- in-warp reduce-scatter of RH values (RH = 8, 16 or 32): afterwards lane l (and the lanes that
+// differ from it only in the low log2(32/RH) bits) holds the warp-wide sum of entry l >> log2(32/RH).
 template <int RH>
 __device__ __forceinline__ double warp_reduce_scatter(double (&v)[RH]) {
+    static_assert(RH == 8 || RH == 16 || RH == 32, "reduce-scatter width");
     const int lane = threadIdx.x & 31;
-    if constexpr (RH == 16) {
-        {
-            const bool hi = lane & 16;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const double send = hi ? v[i] : v[i + 8];
-                const double keep = hi ? v[i + 8] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-        }
-        {
-            const bool hi = lane & 8;
+    for (int h = RH / 2, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
+        const bool hi = lane & bit;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double send = hi ? v[i] : v[i + 4];
-                const double keep = hi ? v[i + 4] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
+        for (int i = 0; i < h; ++i) {
+            const double send = hi ? v[i] : v[i + h];
+            const double keep = hi ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
         }
-        {
-            const bool hi = lane & 4;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const double send = hi ? v[i] : v[i + 2];
-                const double keep = hi ? v[i + 2] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-        }
-        {
-            const bool hi = lane & 2;
-            const double send = hi ? v[0] : v[1];
-            const double keep = hi ? v[1] : v[0];
-            v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-        return v[0];
-    } else {
-        {
-            const bool hi = lane & 16;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double send = hi ? v[i] : v[i + 4];
-                const double keep = hi ? v[i + 4] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-        }
-        {
-            const bool hi = lane & 8;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const double send = hi ? v[i] : v[i + 2];
-                const double keep = hi ? v[i + 2] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-        }
-        {
-            const bool hi = lane & 4;
-            const double send = hi ? v[0] : v[1];
-            const double keep = hi ? v[1] : v[0];
-            v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-        return v[0];
     }
+#pragma unroll
+    for (int bit = 16 / RH; bit >= 1; bit >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], bit);
+    return v[0];
 }
 
 // Tile geometry for at most NVMAX variables and NW warps per CTA.
-template <int NVMAX, int NW_ = 8>
+template <int NVMAX, int NW_ = 8, int KB_ = 1>
 struct GiCfg {
     static constexpr int NW = NW_, NT = 32 * NW_;
+    static constexpr int KB = KB_;                           // constraints projected per search (block size)
+    static constexpr int YB = KB_ > 2 ? KB_ : 2;             // ypart buffers
+    static_assert(KB_ >= 1 && NW_ * KB_ <= 32, "block selection reduces NW*KB candidates in one warp");
     static constexpr int RPW = (NVMAX + NW - 1) / NW;      // rows per warp
     static constexpr int RP = RPW * NW;                      // padded rows
     static constexpr int CS = (NVMAX + 32) / 32;             // column slots per lane (one spare column)
     static constexpr int CP = CS * 32;                       // padded columns
-    static constexpr int RH = (RPW <= 8) ? 8 : 16;           // reduce-scatter width
+    static constexpr int RH = (RPW <= 8) ? 8 : (RPW <= 16 ? 16 : 32);   // reduce-scatter width
     static constexpr int HP = NVMAX * (NVMAX + 1) / 2;       // packed lower triangle
-    static_assert(RPW <= 16, "reduce-scatter network supports up to 16 rows per warp");
+    static_assert(RPW <= 32, "reduce-scatter network supports up to 32 rows per warp");
     static_assert(NVMAX < CP, "need one spare padded column for the piggy-backed scalar");
     __host__ __device__ static constexpr int hp(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 };
@@ -133,15 +115,16 @@ struct GiSm {
     alignas(16) double x[G::RP];
     double g[G::RP];
     double Hp[G::HP];                  // packed lower triangle of H (drops, refresh, fval)
-    double ypart[2][G::NW][G::CP];     // cross-warp partial sums of M'v (double-buffered)
+    double ypart[G::YB][G::NW][G::CP]; // cross-warp partial sums of M'v (double-buffered; one buffer per block member)
     double colk[2][G::RP];             // column broadcast (factorisation / column q / drop column)
     double rowv[G::RP];                // per-warp row vector scratch (gradient / H k)
-    double nvec[G::RP];                // per-warp rows of the normal of the constraint being added
+    double nvec[G::KB][G::RP];         // per-warp rows of the normals of the block's constraints
     double zrow[G::RP];                // per-warp reduced z
     double wpart[3][G::RP];            // symv partials
     double dvec[G::RP];                // LDL' pivots
     double red_val[2][G::NW];
-    int red_idx[2][G::NW];
+    unsigned long long red_key[2][G::NW * G::KB];   // per-warp top-KB violations (dkey) ...
+    int red_idx[2][G::NW * G::KB];                  // ... and their slot*2 + side codes
     int act[G::RP];                    // slot*2 + (side > 0) of working-set column j
     int8_t status[NSLOT + 8];          // -1 / 0 / +1 per slot
 };
@@ -202,8 +185,9 @@ struct GiOps {
             for (int r = 0; r < RPW; ++r) zp[r] += m[r][s] * yj;
         }
         const double zr = warp_reduce_scatter<RH>(zp);
-        const int rr = (RH == 16) ? (lane >> 1) : (lane >> 2);
-        const bool writer = (RH == 16) ? ((lane & 1) == 0) : ((lane & 3) == 0);
+        constexpr int SH = (RH == 32) ? 0 : (RH == 16 ? 1 : 2);
+        const int rr = lane >> SH;
+        const bool writer = (lane & ((1 << SH) - 1)) == 0;
         if (writer && rr < RPW) S.zrow[row0 + rr] = zr;
         __syncwarp();
     }
@@ -250,7 +234,7 @@ struct GiOps {
             __syncthreads();
             const double piv = S.colk[buf][k];
             ok = ok && (piv > 0.0);
-            const double rp = 1.0 / piv;
+            const double rp = __drcp_rn(piv);      // correctly rounded, same value as 1.0 / piv
             if (tid == 0) S.dvec[k] = piv;
             double lj[CS];
 #pragma unroll
@@ -335,42 +319,100 @@ struct GiOps {
         __syncthreads();                           // x complete
     }
 
+    // y_c = M' n_c for the nc <= KB normals in S.nvec (per-warp rows): ONE pass over the tiles and ONE
+    // barrier for the whole block; identical results in every warp.
+    __device__ __forceinline__ static void matvec_T_multi(SM& S, const double (&m)[RPW][CS], int nc,
+                                                          double (&y)[G::KB][CS]) {
+        constexpr int KB = G::KB;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row0 = warp * RPW;
+#pragma unroll
+        for (int c = 0; c < KB; ++c) {
+            if (c < nc) {
+                double yp[CS];
+#pragma unroll
+                for (int s = 0; s < CS; ++s) yp[s] = 0.0;
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    const double v = S.nvec[c][row0 + r];
+#pragma unroll
+                    for (int s = 0; s < CS; ++s) yp[s] = fma(m[r][s], v, yp[s]);
+                }
+#pragma unroll
+                for (int s = 0; s < CS; ++s) S.ypart[c][warp][lane + 32 * s] = yp[s];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < KB; ++c) {
+#pragma unroll
+            for (int s = 0; s < CS; ++s) {
+                double acc = 0.0;
+                if (c < nc) {
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) acc += S.ypart[c][w][lane + 32 * s];
+                }
+                y[c][s] = acc;
+            }
+        }
+    }
+
     // The dual active-set loop.  On entry: M, lam, q consistent with S.act/S.status, S.x the
     // minimiser on that working set, barrier passed.  On exit S.x is the solution (barrier passed).
+    //
+    // Block selection: one search yields the KB most violated constraint sides; ONE pass over the
+    // register tiles projects all their normals (y_c = M'n_c).  The first goes through the full
+    // Goldfarb-Idnani step (partial steps / drops included); the others "piggy-back": every update
+    // of M is a column operation M <- M T, so their projections follow as y_c <- T'y_c (O(nV) per
+    // lane + one warp reduction) and their violations as s_c += t n_c'z = t (y2 . y2_c).  A
+    // piggy-backed add needs no block barrier at all (z, x rows and tile updates are warp-local).
+    // A piggy-backed candidate that is no longer violated is skipped; one that would need a partial
+    // step ends the block (the next search finds it again).
     template <class Prob>
     __device__ static GiStats solve(const Prob& prob, SM& S, double (&m)[RPW][CS], double (&lam)[CS], int& q,
                                     int& ybuf, int nV, double tol, int max_iter) {
+        constexpr int KB = G::KB;
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row0 = warp * RPW;
         GiStats st = {0, GI_EXIT_SOLVED, 0, 0, 0};
         int rbuf = 0;
         PHASE_DECL;
         while (true) {
-            // P1: most violated inactive constraint side (policy evaluates its slots)
-            double best = 0.0;
-            int best_i = 0x7fffffff;
-            PHASE(0);
-            prob.search(best, best_i);
-            PHASE(1);
+            // P1: the KB most violated inactive constraint sides (policy evaluates its slots; one
+            // candidate per thread)
+            double cviol[KB];
+            int ccode[KB];
+            {
+                double best = 0.0;
+                int best_i = 0x7fffffff;
+                PHASE(0);
+                PHASE_COUNT(12);
+                prob.search(best, best_i);
+                PHASE(1);
+                unsigned long long key = dkey(best);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-                if (ov < best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
-            }
-            if (lane == 0) { S.red_val[rbuf][warp] = best; S.red_idx[rbuf][warp] = best_i; }
-            __syncthreads();
-            double viol = S.red_val[rbuf][0];
-            int pcode = S.red_idx[rbuf][0];
+                for (int c = 0; c < KB; ++c) {
+                    unsigned long long km;
+                    const int wl = warp_argmin_key(key, km);
+                    const int wi = __shfl_sync(0xffffffffu, best_i, wl);
+                    if (lane == 0) { S.red_key[rbuf][warp * KB + c] = km; S.red_idx[rbuf][warp * KB + c] = wi; }
+                    if (lane == wl) key = DKEY_NONE;
+                }
+                __syncthreads();
+                unsigned long long ck = DKEY_NONE;
+                int ci = 0x7fffffff;
+                if (lane < NW * KB) { ck = S.red_key[rbuf][lane]; ci = S.red_idx[rbuf][lane]; }
+                rbuf ^= 1;
 #pragma unroll
-            for (int w = 1; w < NW; ++w) {
-                const double ov = S.red_val[rbuf][w];
-                const int oi = S.red_idx[rbuf][w];
-                if (ov < viol || (ov == viol && oi < pcode)) { viol = ov; pcode = oi; }
+                for (int c = 0; c < KB; ++c) {
+                    unsigned long long km;
+                    const int wl = warp_argmin_key(ck, km);
+                    ccode[c] = __shfl_sync(0xffffffffu, ci, wl);
+                    cviol[c] = dkey_inv(km);
+                    if (lane == wl) ck = DKEY_NONE;
+                }
             }
-            rbuf ^= 1;
             PHASE(2);
 
-            if (!(viol < -tol)) {
+            if (!(cviol[0] < -tol)) {
                 // the refresh repairs what chains of partial steps leave behind; a run of pure
                 // full steps keeps x the exact working-set minimiser (to round-off)
                 if (st.n_refresh >= 1 || st.n_drop == 0) break;
@@ -392,28 +434,48 @@ struct GiOps {
                 __syncthreads();                   // x complete
                 continue;
             }
-            const int pslot = pcode >> 1, pside = (pcode & 1) ? +1 : -1;
-            double sp = viol;                                   // n'x - b  (< 0)
-            double lam_p = 0.0;
-            // P2: this warp's entries of the normal
-            {
-                const auto prep = prob.normal_prepare(pslot, pside);      // warp-uniform part
-                if (lane < RPW) {
-                    const int i = row0 + lane;
-                    S.nvec[i] = (i < nV) ? prob.normal_entry(prep, i) : 0.0;
+            int nleft = 0;                          // candidates (sorted by violation: a prefix is valid)
+#pragma unroll
+            for (int c = 0; c < KB; ++c) nleft += (cviol[c] < -tol) ? 1 : 0;
+            if (q + nleft > nV) nleft = nV - q > 0 ? nV - q : 1;
+
+            // P2: this warp's entries of the block's normals
+#pragma unroll
+            for (int c = 0; c < KB; ++c) {
+                if (c < nleft) {
+                    const auto prep = prob.normal_prepare(ccode[c] >> 1, (ccode[c] & 1) ? +1 : -1);   // warp-uniform part
+                    if (lane < RPW) {
+                        const int i = row0 + lane;
+                        S.nvec[c][i] = (i < nV) ? prob.normal_entry(prep, i) : 0.0;
+                    }
                 }
             }
             __syncwarp();
-            const double nn = prob.norm2(pslot);
             PHASE(3);
 
-            bool failed = false;
+            // P3: project the block.  A single variable bound has n = +-e_p, so y is +-(row p of M):
+            // the owning warp publishes its row, nobody multiplies or sums partials.
+            double yq[KB][CS];                      // queue of projections; yq[0] is the current candidate
+            bool fresh = true;                      // yq[0] is valid for the current candidate
+            if (KB == 1 || nleft == 1) {
+                fresh = false;
+            } else {
+                matvec_T_multi(S, m, nleft, yq);
+            }
+            PHASE(4);
+
+            int pslot = ccode[0] >> 1, pside = (ccode[0] & 1) ? +1 : -1;
+            double sp = cviol[0];                   // n'x - b  (< 0)
+            double lam_p = 0.0;
+            double nn = prob.norm2(pslot);
+            bool piggy = false, dropped = false, failed = false;
             while (true) {
                 if (++st.iters > max_iter) { st.exitflag = GI_EXIT_MAXITER; failed = true; break; }
-                // P3: y = M' n.  For a variable bound n = +-e_p, so y is +-(row p of M): the owning
-                // warp publishes its row, nobody multiplies or sums partials.
-                double y[CS], dummy;
-                if (prob.is_unit(pslot)) {
+                double y[CS];
+                if (fresh) {
+#pragma unroll
+                    for (int s = 0; s < CS; ++s) y[s] = yq[0][s];
+                } else if (prob.is_unit(pslot)) {
                     const int pr = pslot - row0;               // warp-uniform
                     if (pr >= 0 && pr < RPW) {
 #pragma unroll
@@ -429,9 +491,11 @@ struct GiOps {
                     for (int s = 0; s < CS; ++s) y[s] = sgn * S.ypart[ybuf][0][lane + 32 * s];
                     ybuf ^= 1;
                 } else {
-                    matvec_T(S, m, ybuf, S.nvec, 0.0, y, dummy);
+                    double dummy;
+                    matvec_T(S, m, ybuf, S.nvec[0], 0.0, y, dummy);
                 }
-                PHASE(4);
+                fresh = false;
+                PHASE(5);
                 // P4 (every warp, redundantly): step lengths
                 double d2 = 0.0, t1 = INFINITY;
                 int l = -1;
@@ -449,22 +513,21 @@ struct GiOps {
                 }
                 d2 = warp_sum_d(d2);
                 {
-                    double tm = t1;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) tm = fmin(tm, __shfl_xor_sync(0xffffffffu, tm, o));
-                    const unsigned who = __ballot_sync(0xffffffffu, l >= 0 && t1 == tm);
-                    if (who) l = __shfl_sync(0xffffffffu, l, __ffs(who) - 1);
-                    t1 = tm;
+                    unsigned long long km;
+                    const int wl = warp_argmin_key(dkey(t1), km);
+                    l = __shfl_sync(0xffffffffu, l, wl);
+                    t1 = dkey_inv(km);
                 }
                 const bool lin_dep = !(d2 > 1e-13 * fmax(1.0, nn));
                 const double inv_d2 = __drcp_rn(d2);
                 const double t2 = lin_dep ? INFINITY : (sp < 0.0 ? -sp * inv_d2 : 0.0);
-                if (isinf(t1) && isinf(t2)) { st.exitflag = GI_EXIT_INFEASIBLE; failed = true; break; }
                 const bool full = (t2 <= t1);
+                if (piggy && !full) { --st.iters; PHASE_COUNT(14); break; }          // left to the next search
+                if (isinf(t1) && isinf(t2)) { st.exitflag = GI_EXIT_INFEASIBLE; failed = true; break; }
                 const bool primal = !isinf(t2);
                 const double t = full ? t2 : t1;
-                PHASE(5);
-                // P5: z = J2 y2, x += t z
+                PHASE(6);
+                // P5: z = J2 y2, x += t z  (this warp's rows only)
                 if (primal) {
                     matvec_N(S, m, y, q, nV);
                     if (lane < RPW) {
@@ -473,15 +536,10 @@ struct GiOps {
                     }
                     sp += t * d2;
                 }
-                if (full) {
-                    // bookkeeping of the add happens BEFORE the barrier that publishes x, so the
-                    // next search (which follows the register-only update below without another
-                    // barrier) sees a consistent x / status
-                    if (tid == 0) {
-                        S.act[q] = pslot * 2 + (pside > 0 ? 1 : 0);
-                        S.status[pslot] = (int8_t)pside;
-                    }
-                    __syncthreads();               // x complete
+                if (full && tid == 0) {
+                    // bookkeeping of the add; published by the barrier that ends the block
+                    S.act[q] = pslot * 2 + (pside > 0 ? 1 : 0);
+                    S.status[pslot] = (int8_t)pside;
                 }
 #pragma unroll
                 for (int s = 0; s < CS; ++s) {
@@ -489,7 +547,7 @@ struct GiOps {
                     if (j < q) lam[s] -= t * y[s];
                 }
                 lam_p += t;
-                PHASE(6);
+                PHASE(7);
                 if (full) {
                     // P6a: add p.  K1 <- K1 - k r', J2 <- J2 (I - beta v v'), column q <- k = z/d2
                     const int qs = q >> 5, ql = q & 31;
@@ -507,9 +565,9 @@ struct GiOps {
 #pragma unroll
                     for (int s = 0; s < CS; ++s)
                         if (s == qs) yq_l = y[s];
-                    const double yq = __shfl_sync(0xffffffffu, yq_l, ql);
-                    const double sgd = (yq >= 0.0) ? delta : -delta;
-                    const double beta = __drcp_rn(d2 + fabs(yq) * delta);
+                    const double yqv = __shfl_sync(0xffffffffu, yq_l, ql);
+                    const double sgd = (yqv >= 0.0) ? delta : -delta;
+                    const double beta = __drcp_rn(d2 + fabs(yqv) * delta);
                     // new = c*cur - kr*ya - wr*yb with (c, ya, yb) = (1, y, 0) for j < q,
                     // (0, -1, 0) for j == q, (1, 0, y) for j > q: no per-element selects
                     double cc[CS], ya[CS], yb[CS];
@@ -533,14 +591,67 @@ struct GiOps {
                         const int j = lane + 32 * s;
                         if (j == q) lam[s] = lam_p;
                     }
-                    ++q;
                     ++st.n_add;
                     __syncwarp();
-                    PHASE(7);
-                    break;
+                    PHASE(8);
+                    if (KB == 1 || dropped || nleft <= 1) { ++q; break; }
+                    // the column operation applied to the projections still queued:
+                    //   j < q : y_j - kappa y_j^p,  j = q : kappa,  j > q : y_j - omega y_j^p
+                    //   kappa = (y2 . y2^p)/d2,  omega = beta (y2 . y2^p + sgd y_q);  s += t (y2 . y2^p)
+#pragma unroll
+                    for (int c = 1; c < KB; ++c) {
+                        if (c < nleft) {
+                            double part = 0.0, yc_q = 0.0;
+#pragma unroll
+                            for (int s = 0; s < CS; ++s) {
+                                const int j = lane + 32 * s;
+                                part = fma((j >= q && j < nV) ? y[s] : 0.0, yq[c][s], part);
+                                if (s == qs) yc_q = yq[c][s];
+                            }
+                            const double c12 = warp_sum_d(part);
+                            yc_q = __shfl_sync(0xffffffffu, yc_q, ql);
+                            const double kappa = c12 * inv_d2;
+                            const double omega = beta * (c12 + sgd * yc_q);
+#pragma unroll
+                            for (int s = 0; s < CS; ++s) {
+                                const int j = lane + 32 * s;
+                                const double co = (j < q) ? kappa : omega;
+                                const double v = fma(-co, y[s], yq[c][s]);
+                                yq[c][s] = (j == q) ? kappa : v;
+                            }
+                            cviol[c] += t * c12;
+                        }
+                    }
+                    ++q;
+                    // next candidate that is still violated
+                    bool more = false;
+                    while (nleft > 1) {
+#pragma unroll
+                        for (int c = 0; c + 1 < KB; ++c) {
+                            cviol[c] = cviol[c + 1];
+                            ccode[c] = ccode[c + 1];
+#pragma unroll
+                            for (int s = 0; s < CS; ++s) yq[c][s] = yq[c + 1][s];
+                        }
+                        --nleft;
+                        if (cviol[0] < -tol) { more = true; break; }
+                        PHASE_COUNT(15);
+                    }
+                    if (!more || q >= nV) break;
+                    pslot = ccode[0] >> 1;
+                    pside = (ccode[0] & 1) ? +1 : -1;
+                    sp = cviol[0];
+                    lam_p = 0.0;
+                    nn = prob.norm2(pslot);
+                    piggy = true;
+                    fresh = true;
+                    PHASE_COUNT(13);
+                    PHASE(9);
+                    continue;
                 }
                 // P6b: drop active constraint l (column l of K1)
                 {
+                    dropped = true;
                     const int ls = l >> 5, ll = l & 31;
                     if (lane == ll) {
 #pragma unroll
@@ -601,10 +712,11 @@ struct GiOps {
                     }
                     --q;
                     ++st.n_drop;
-                    PHASE(8);
+                    PHASE(10);
                 }
             }
             if (failed) break;
+            __syncthreads();                       // x, act, status of the whole block published
         }
         __syncthreads();
         PHASE_FLUSH;

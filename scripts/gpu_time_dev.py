@@ -34,3 +34,9 @@ for _ in range(K): mpc.ltvmpc_dev(mid, B, N, 0.05, ptrs, stream=mpc.stream)
 e1.record(st); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 print(f"{model} B={B} kv={os.environ.get('FSAE_KV','2')}: {ms:.2f} ms/step -> {B/ms*1e3:.0f} QP/s ; exit!=0 {(o['exitflag']!=0).sum().item()} iters {o['iters'].double().mean().item():.1f}")
+if os.environ.get("FSAE_KV"):
+    u_kv = o['u_opt'].clone(); f_kv = o['fval'].clone()
+    mpc.set_kernel_version(1)            # shared-memory cross-check kernel
+    mpc.ltvmpc_dev(mid, B, N, 0.05, ptrs, stream=mpc.stream); torch.cuda.synchronize()
+    du = (u_kv - o['u_opt']).abs().max().item(); df = ((f_kv - o['fval']).abs() / (1 + o['fval'].abs())).max().item()
+    print(f"   vs v1 kernel: max|du| {du:.3e}  max rel dfval {df:.3e}")

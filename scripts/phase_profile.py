@@ -6,7 +6,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 prof_so = os.path.join(ROOT, "build", "libfsae_prof.so")
-if not os.path.exists(prof_so):
+if not os.path.exists(prof_so) or os.path.getmtime(prof_so) < max(os.path.getmtime(os.path.join(ROOT, "fsae_mpc_b200", "csrc", f)) for f in os.listdir(os.path.join(ROOT, "fsae_mpc_b200", "csrc"))):
     os.makedirs(os.path.dirname(prof_so), exist_ok=True)
     subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DFSAE_PROFILE", "-shared",
                     "-Xcompiler", "-fPIC", "-o", prof_so, os.path.join(ROOT, "fsae_mpc_b200", "csrc", "capi.cu")], check=True)
@@ -16,22 +16,33 @@ import fsae_mpc_b200 as fm
 from fsae_mpc_b200 import workload as wl
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 mpc = fm.FsaeMpc(0)
+if os.environ.get("FSAE_KV"): mpc.set_kernel_version(int(os.environ["FSAE_KV"]))
 for tid, (n, t) in enumerate(wl.load_tracks().items()):
     mpc.set_track(tid, t[0], t[1], t[2])
 lib = mpc._lib
 lib.fsae_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
+lib.fsae_profile_read_stages.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
+sg = (C.c_uint64 * 16)()
 x0, xr, xl, ul = wl.perturbed_batch("kinematic", "fsg2019", B, 0)
 out = (C.c_uint64 * 16)()
 mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, 0.05, xl, ul)
 lib.fsae_profile_read(mpc._ctx, out, 1)
 mpc.counters(reset=True)
+lib.fsae_profile_read_stages(mpc._ctx, sg, 1)
 r = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, 0.05, xl, ul)
 lib.fsae_profile_read(mpc._ctx, out, 1)
 adds, drops, refr = mpc.counters()
-names = ["loop/refresh overhead", "P1 search (policy)", "P1 argmin+barrier", "P2 normal", "P3 y=M'n (+barrier)", "P4 step lengths",
-         "P5 z=J2y2, x update (+barrier)", "P6a add update", "P6b drop"]
-tot = sum(out[i] for i in range(9))
+names = ["loop/refresh/end-of-block barrier", "P1 search (policy)", "P1 top-KB argmin+barrier", "P2 normals", "P3 block projection Y=M'N (+barrier)",
+         "P3' y from queue / re-projection", "P4 step lengths", "P5 z=J2y2, x update", "P6a add update", "queue transform + advance", "P6b drop"]
+tot = sum(out[i] for i in range(11))
+print(f"searches/QP {out[12]/B:.1f}  piggy-backed adds/QP {out[13]/B:.1f}  piggy aborts (partial step)/QP {out[14]/B:.2f}  skipped (no longer violated)/QP {out[15]/B:.2f}")
 it = r.iters.sum()
 print(f"B={B}: iterations {it} (adds {adds}, drops {drops}), cycles in loop per QP {tot/B:.0f}, per iteration {tot/it:.0f}")
 for i, n in enumerate(names):
     print(f"  {n:34s} {out[i]/it:8.0f} cyc/iter  {100*out[i]/tot:5.1f}%")
+lib.fsae_profile_read_stages(mpc._ctx, sg, 1)
+snames = ["load (TMA)", "linearise", "free response + B_bar chains", "g, bounds, row norms", "H build", "factor + layout", "initial point", "active-set loop", "outputs"]
+stot = sum(sg[i] for i in range(9))
+print(f"kernel stages, cycles per QP (tid 0): total {stot/B:.0f}")
+for i, n in enumerate(snames):
+    print(f"  {n:34s} {sg[i]/B:9.0f} cyc  {100*sg[i]/stot:5.1f}%")
