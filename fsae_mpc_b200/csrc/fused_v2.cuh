@@ -48,9 +48,15 @@ struct SmemV2 {
     double gram[ROWNORMS ? N * NGR : 1];            // per step: Gram matrix of the constraint B_bar rows
     double csum[ROWNORMS ? N * C::NCR * D::NU : 1]; // per step: their sums over each control's columns
     double dd[N * D::NX];
+    double Gs[N * D::NU * D::NX];      // G_s = B' W_{s+1}: cost Gramian seen from the controls of step s
+    double Kc[N * D::NU * D::NX];      // Riccati feedback gains K_s (closed-loop chains -> J)
+    double Wi[N * D::NU * D::NU];      // (Lambda_s)^(-T/2) / sqrt(2): the diagonal blocks of J
+    double Lam3[N * 3];                // Lambda_s (a, b, d)
+    double wgram[6 * D::NX * D::NX + 3 * D::NU * D::NX];   // recursion scratch: W, P (double-buffered), W A, P A; B'P, S, K
     double scal[8];                    // 0 cost const
     alignas(8) fsae_params prm;        // this problem's parameter set (copied once: no global loads in the loops)
     alignas(8) unsigned long long mbar; // mbarrier of the input staging
+    int prog;                          // last horizon stage the backward recursion has published (N: none yet)
 };
 
 // ---- TMA (bulk async copy) staging of one problem's contiguous input records ----------------
@@ -253,6 +259,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             }
         }
         for (int i = tid; i < D::NSLOT; i += NT) S.gi.status[i] = 0;
+        if (tid == 0) S.prog = N;
         for (int i = tid; i < KB_ * RP; i += NT) (&S.gi.nvec[0][0])[i] = 0.0;
         for (int i = tid; i < RP; i += NT) { S.gi.x[i] = 0.0; S.gi.g[i] = 0.0; S.gi.rowv[i] = 0.0; S.gi.zrow[i] = 0.0; S.gi.colk[0][i] = 0.0; S.gi.colk[1][i] = 0.0; }
         if (aligned) {
@@ -291,6 +298,151 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
 
     STAGE(1);
     // ---------------------------------------------------------------- free response + B_bar chains
+    // Three things run side by side on different warps:
+    //  * warps 0..2: the columns of B_bar (v <- A_k v), packed block-lower-triangular
+    //  * warp GW   : the cost Gramian along the horizon, backwards:  W_N = Q_N,
+    //                W_s = Q + A_s' W_{s+1} A_s,  G_s = B' W_{s+1}.  With it every entry of
+    //                H = 2 (B_bar' Qbar B_bar + Rbar) is ONE short dot product (H stage below)
+    //                instead of a sum over the remaining horizon:
+    //                H_ij / 2 = e_ci' B' W_{s+1} x^(j)_{s+1},  s = step of the later control i
+    //  * warp NW-1 : the free response x_f = A_bar x0 + d_bar
+    // With five or more warps the recursion warp runs beside everything else: the other warps
+    // ("workers") go on to g / bounds / row norms behind a named barrier of their own and then
+    // follow the recursion stage by stage (adjoint rows of J, below); all meet before the tiles
+    // are filled.  With four warps the recursion shares the free-response warp and nothing overlaps.
+    static_assert(NW >= 4, "stage map: three chain warps + the free-response warp");
+    constexpr bool OVL = NW >= 5;
+    constexpr int GW = OVL ? 3 : NW - 1;
+    constexpr int WNT = OVL ? NT - 32 : NT;                      // worker threads
+    const bool worker = !OVL || warp != GW;
+    const int wtid = (OVL && warp > GW) ? tid - 32 : tid;        // worker index
+    auto wbar = [&]() {
+        if (OVL) asm volatile("bar.sync 1, %0;" ::"r"(WNT) : "memory");
+        else __syncthreads();
+    };
+    if (warp == GW) {
+        // Two backward recursions share the pass (s = N-1 .. 0):
+        //   Gramian  W_s = Q + A_s' W_{s+1} A_s                      -> G_s = B' W_{s+1}   (entries of H)
+        //   Riccati  P_s = Q + A_s' P_{s+1} A_s - S' Lambda^-1 S,  Lambda = R + B' P_{s+1} B,
+        //            S = B' P_{s+1} A_s,  K_s = -Lambda^-1 S
+        // The Riccati identity  u'(B_bar' Qbar B_bar + Rbar) u = sum_s |Lambda_s^(1/2) (u_s - K_s x_s)|^2
+        // makes J = T^-1 / sqrt 2 (J'HJ = I) the closed-loop response to unit "innovations":
+        // u_s = K_s x_s + Lambda_s^(-T/2) v_s.  No dense factorisation of H is needed.
+        static_assert(NU == 2, "2 x 2 Lambda blocks are inverted in closed form");
+        constexpr int NN = NX * NX, NB = NU * NX, NR_ = C::NREAL;
+        double* Wb = S.wgram;               // [2][NN]
+        double* Pb = S.wgram + 2 * NN;      // [2][NN]
+        double* TW = S.wgram + 4 * NN;      // W A
+        double* TP = S.wgram + 5 * NN;      // P A
+        double* BP = S.wgram + 6 * NN;      // B'P            [NU][NX]
+        double* Sm = BP + NB;               // S = B'P A      [NU][NX]
+        double* Kx = Sm + NB;               // K              [NU][NX]
+        for (int e = lane; e < NN; e += 32) {
+            const double v = (e / NX == e % NX) ? P.Q_terminal[e / NX] : 0.0;
+            Wb[e] = v;
+            Pb[e] = v;
+        }
+        __syncwarp();
+        int cur = 0;
+        RSTAGE_DECL;
+        // Three warp-synchronous phases per stage; every lane runs the same instruction stream on its own
+        // entry (indices clamped, stores predicated), the dot products of a phase are independent chains.
+        for (int st = N - 1; st >= 0; --st) {
+            const double* W = Wb + cur * NN;
+            const double* Pm = Pb + cur * NN;
+            const double* As = S.Ad + st * NR_ * NX;          // rows of the real states; integrator rows are unit rows
+            // phase 1: W A, P A (entry (i, j));  B'P, G_s = B'W (entry (c = i, j), i < NU)
+            for (int e0 = 0; e0 < NN; e0 += 32) {
+                const int e = (e0 + lane < NN) ? e0 + lane : 0;
+                const int i = e / NX, j = e - i * NX, c = i < NU ? i : NU - 1;
+                double tw = (j >= NR_) ? W[i * NX + j] : 0.0, tp = (j >= NR_) ? Pm[i * NX + j] : 0.0, bp = 0.0, wb = 0.0;
+#pragma unroll
+                for (int l = 0; l < NX; ++l) {
+                    const double bl = S.B1[l * NU + c];
+                    bp = fma(bl, Pm[l * NX + j], bp);
+                    wb = fma(bl, W[l * NX + j], wb);
+                    if (l < NR_) {
+                        const double al = As[l * NX + j];
+                        tw = fma(W[i * NX + l], al, tw);
+                        tp = fma(Pm[i * NX + l], al, tp);
+                    }
+                }
+                if (e0 + lane < NN) { TW[e] = tw; TP[e] = tp; }
+                if (e0 + lane < NB) { BP[e] = bp; S.Gs[(st * NU + c) * NX + j] = wb; }
+            }
+            __syncwarp();
+            RSTAGE(0);
+            // phase 2 (lane = (c, j), c < NU): S = (B'P) A column j, Lambda = R + (B'P) B, K = -Lambda^-1 S
+            {
+                const int e = lane < NB ? lane : 0;
+                const int c = e / NX, j = e - c * NX;
+                double s0 = (j >= NR_) ? BP[j] : 0.0, s1 = (j >= NR_) ? BP[NX + j] : 0.0;
+                double la = P.R[0], lb = 0.0, ld = P.R[1];
+#pragma unroll
+                for (int l = 0; l < NX; ++l) {
+                    const double b0 = BP[l], b1 = BP[NX + l];
+                    la = fma(b0, S.B1[l * NU + 0], la);
+                    lb = fma(b0, S.B1[l * NU + 1], lb);
+                    ld = fma(b1, S.B1[l * NU + 1], ld);
+                    if (l < NR_) {
+                        const double al = As[l * NX + j];
+                        s0 = fma(b0, al, s0);
+                        s1 = fma(b1, al, s1);
+                    }
+                }
+                const double rdet = __drcp_rn(fma(la, ld, -lb * lb));
+                const double kv = (c == 0) ? (lb * s1 - ld * s0) * rdet : (lb * s0 - la * s1) * rdet;
+                if (lane < NB) {
+                    Sm[e] = (c == 0) ? s0 : s1;
+                    Kx[e] = kv;
+                    S.Kc[(st * NU + c) * NX + j] = kv;
+                }
+                if (lane < 3) S.Lam3[st * 3 + lane] = (lane == 0) ? la : (lane == 1 ? lb : ld);
+            }
+            __syncwarp();
+            if (lane == 0) {                       // K_st and G_st are in shared memory: publish the stage
+                __threadfence_block();
+                *(volatile int*)&S.prog = st;
+            }
+            RSTAGE(1);
+            if (st == 0) break;
+            // phase 3: W' = Q + A'(W A),  P' = Q + A'(P A) + S'K
+            double* Wn = Wb + (cur ^ 1) * NN;
+            double* Pn = Pb + (cur ^ 1) * NN;
+            for (int e0 = 0; e0 < NN; e0 += 32) {
+                const int e = (e0 + lane < NN) ? e0 + lane : 0;
+                const int i = e / NX, j = e - i * NX;
+                const double qd = (i == j) ? P.Q[i] : 0.0;
+                double aw = qd + ((i >= NR_) ? TW[i * NX + j] : 0.0);
+                double ap = qd + ((i >= NR_) ? TP[i * NX + j] : 0.0);
+                double sk = 0.0;
+#pragma unroll
+                for (int l = 0; l < NR_; ++l) {
+                    const double al = As[l * NX + i];
+                    aw = fma(al, TW[l * NX + j], aw);
+                    ap = fma(al, TP[l * NX + j], ap);
+                }
+#pragma unroll
+                for (int c = 0; c < NU; ++c) sk = fma(Sm[c * NX + i], Kx[c * NX + j], sk);
+                if (e0 + lane < NN) { Wn[e] = aw; Pn[e] = ap + sk; }
+            }
+            __syncwarp();
+            RSTAGE(2);
+            cur ^= 1;
+        }
+        // Lambda_s^(-T/2) / sqrt 2 for every stage (off the recursion's critical path).  Lambda = G G',
+        // G = [l11 0; l21 l22]:  G^-T = [1/l11  -l21/(l11 l22); 0  1/l22]
+        for (int st = lane; st < N; st += 32) {
+            const double la = S.Lam3[st * 3], lb = S.Lam3[st * 3 + 1], ld = S.Lam3[st * 3 + 2];
+            const double i11 = rsqrt(la), l21 = lb * i11;
+            const double i22 = rsqrt(fma(-l21, l21, ld));
+            const double r2 = 0.70710678118654752440;
+            S.Wi[st * 4 + 0] = r2 * i11;
+            S.Wi[st * 4 + 1] = -r2 * l21 * i11 * i22;
+            S.Wi[st * 4 + 2] = 0.0;
+            S.Wi[st * 4 + 3] = r2 * i22;
+        }
+    }
     if (warp == NW - 1) {
         if (lane == 0) {
             double xp[NX], xn[NX];
@@ -315,8 +467,9 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
                 }
             }
         }
-    } else {
-        for (int t = tid; t < N * NU; t += NT - 32) {
+    }
+    if (tid < 96) {
+        for (int t = tid; t < N * NU; t += 96) {
             const int i = t / NU, c = t - i * NU;
             double v[NX], vn[NX];
 #pragma unroll
@@ -340,17 +493,17 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             }
         }
     }
-    __syncthreads();
+    if (worker) wbar();        // B_bar and the free response are complete
 
     STAGE(2);
     // ---------------------------------------------------------------- g, bounds, row norms, cost const
-    {
+    if (worker) {
         double* e = S.dd;      // tracking error overwrites dd (dead after the free response)
-        for (int i = tid; i < NX * N; i += NT) e[i] = S.xf[i] - S.xr[i];
+        for (int i = wtid; i < NX * N; i += WNT) e[i] = S.xf[i] - S.xr[i];
         if (S_t::ROWNORMS) {
             // per-step Gram matrix / column sums of the B_bar rows the constraints touch: the squared
             // norm of every row normal then has a closed form (below)
-            for (int k = NT - 1 - tid; k < N; k += NT) {      // the last threads: the first ones have the longest g sums
+            for (int k = WNT - 1 - wtid; k < N; k += WNT) {      // the last threads: the first ones have the longest g sums
                 double G[S_t::NGR], Sm[C::NCR * NU];
 #pragma unroll
                 for (int i = 0; i < S_t::NGR; ++i) G[i] = 0.0;
@@ -377,8 +530,8 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
                 for (int i = 0; i < C::NCR * NU; ++i) S.csum[k * C::NCR * NU + i] = Sm[i];
             }
         }
-        __syncthreads();
-        for (int j = tid; j < nV; j += NT) {
+        wbar();
+        for (int j = wtid; j < nV; j += WNT) {
             double acc = 0.0;
             if (j < nU) {
                 const int sj = j / NU, cj = j - sj * NU;
@@ -414,7 +567,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             acc = warp_sum(acc);
             if (lane == 0) S.scal[0] = acc;
         }
-        for (int t = tid; t < D::NROWS; t += NT) {
+        for (int t = wtid; t < D::NROWS; t += WNT) {
             const int r = t / N, k = t - r * N;
             double lo, up;
             C::row_bounds(r, S.xf + k * NX, S.xl + k * NX, S.ul + k * NU, S.pc + k * C::NPC, S.g0 + k * C::NG0, S.cg, P, lo, up);
@@ -454,101 +607,135 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             }
             S.rn2[t] = n2;
         }
-    }
 
-    STAGE(3);
-    // ---------------------------------------------------------------- H in register tiles
-    // generate_qp.m:29  H = 2 (B' Qbar B + Rbar) accumulated as a sum of rank-1 terms
-    // q_{k,c} b_{k,c} b_{k,c}' over the rows (k, c) of B_bar, directly into the tile layout.
-    double m[RPW][CS];
+        // Rows of J, following the recursion: row t = (k, cu) is  e_cu' K_k Acl_{k-1} .. Acl_{m+1} B Lambda_m^(-T/2)
+        // at the columns of stage m < k (Acl = A + B K), and Lambda_k^(-T/2) on the diagonal block (the
+        // 2 x 2 factor Lambda_m^(-T/2) / sqrt 2 of every column pair is applied when the tiles are filled).  The
+        // adjoint  lam <- lam Acl_m  runs in the SAME direction as the Riccati recursion, so each row
+        // thread advances one stage as soon as that stage is published.  Staged packed (like B_bar)
+        // in the region that later holds the packed H.
+        {
+            static_assert(NU * D::NPK <= D::HP, "J staging must fit the packed-H region");
+            static_assert(WNT >= nU, "one worker thread per row of J");
+            double* Jst = S.gi.Hp;
+            const int t = wtid - (WNT - nU);
+            const int wfirst = (WNT - nU) >> 5;                 // first worker warp that owns rows
+            if ((wtid >> 5) >= wfirst) {
+                const int k = t >= 0 ? t / NU : N, cu = t >= 0 ? t - (t / NU) * NU : 0;   // k = N: no row (padding lanes)
+                double lamv[NX];
 #pragma unroll
-    for (int r = 0; r < RPW; ++r)
+                for (int l = 0; l < NX; ++l) lamv[l] = 0.0;
+                for (int mm = N - 1; mm >= 0; --mm) {
+                    while (*(volatile int*)&S.prog > mm) __nanosleep(100);
+                    __threadfence_block();
+                    if (mm == k) {
 #pragma unroll
-        for (int s = 0; s < CS; ++s) m[r][s] = 0.0;
-    {
-        // rows of this warp span controls row0 .. row0+RPW-1; a B_bar row (k, .) is nonzero on
-        // controls j < NU (k+1): skip rows (k) that cannot touch this warp's tile rows.
-        const int kmin = (row0 < nU) ? row0 / NU : N;
-        for (int k = kmin; k < N; ++k) {
-            const int len = NU * (k + 1);
+                        for (int c = 0; c < NU; ++c) Jst[cu * D::NPK + D::pk(k, NU * k + c)] = (c == cu) ? 1.0 : 0.0;
+                        if (k > 0) {
 #pragma unroll
-            for (int ii = 0; ii < C::NREAL; ++ii) {
-                const int rs = C::real_state(ii);
-                const double qk = 2.0 * ((k == N - 1) ? P.Q_terminal[rs] : P.Q[rs]);
-                if (qk == 0.0) continue;
-                const double* brow = S.Bf + ii * D::NPK + D::pk(k, 0);
-                double bj[CS];
+                            for (int l = 0; l < NX; ++l) lamv[l] = S.Kc[(k * NU + cu) * NX + l];
+                        }
+                    } else if (mm < k && k < N) {
+                        double bv[NU];
 #pragma unroll
-                for (int s = 0; s < CS; ++s) {
-                    const int j = lane + 32 * s;
-                    bj[s] = (j < len) ? brow[j] * qk : 0.0;
-                }
+                        for (int r = 0; r < NU; ++r) {
+                            double acc = 0.0;
 #pragma unroll
-                for (int r = 0; r < RPW; ++r) {
-                    const int i = row0 + r;
-                    const double bi = (i < len) ? brow[i] : 0.0;
+                            for (int l = 0; l < NX; ++l) acc = fma(lamv[l], S.B1[l * NU + r], acc);
+                            bv[r] = acc;
+                        }
 #pragma unroll
-                    for (int s = 0; s < CS; ++s) m[r][s] += bi * bj[s];
-                }
-            }
-        }
-        // integrator states (exact prefix rows: dt on their control up to step k) and R
+                        for (int c = 0; c < NU; ++c) Jst[cu * D::NPK + D::pk(k, NU * mm + c)] = bv[c];    // x Lambda_m^(-T/2) at the tile fill
+                        if (mm > 0) {
+                            double ln[NX];
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            const int i = row0 + r;
+                            for (int l = 0; l < NX; ++l) {
+                                double acc = (l >= C::NREAL) ? lamv[l] : 0.0;
 #pragma unroll
-            for (int s = 0; s < CS; ++s) {
-                const int j = lane + 32 * s;
-                if (i < nU && j < nU) {
-                    const int si = i / NU, ci = i - si * NU, sj = j / NU, cj = j - sj * NU;
-                    const int sm = si > sj ? si : sj;
+                                for (int jr = 0; jr < C::NREAL; ++jr) acc = fma(lamv[jr], S.Ad[(mm * C::NREAL + jr) * NX + l], acc);
 #pragma unroll
-                    for (int ii = 0; ii < C::NINT; ++ii) {
-                        if (C::int_ucol(ii) == ci && cj == ci) {
-                            const int rs = C::int_state(ii);
-                            m[r][s] += 2.0 * dt * dt * (P.Q[rs] * (double)(N - 1 - sm) + P.Q_terminal[rs]);
+                                for (int r = 0; r < NU; ++r) acc = fma(bv[r], S.Kc[(mm * NU + r) * NX + l], acc);
+                                ln[l] = acc;
+                            }
+#pragma unroll
+                            for (int l = 0; l < NX; ++l) lamv[l] = ln[l];
                         }
                     }
-                    if (i == j) m[r][s] += 2.0 * P.R[ci];
                 }
             }
         }
     }
-    // packed copy for later symv's (slack diagonal gets flat_eps), optional debug tap
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-        const int i = row0 + r;
+
+    __syncthreads();           // g, bounds, J staging complete
+    STAGE(3);
+    // ---------------------------------------------------------------- operator tiles, packed H
+    // M = [ e_{nU}, .., e_{nU+NS-1} | J ]: the NS flat (zero-curvature) slack variables start with their
+    // lower bound in the working set (q = NS, lam = R_soft: dual feasible), J (J'HJ = I) from the staging.
+    using Ops = GiOps<G, GiSm<G, D::NSLOT>>;
+    GiSm<G, D::NSLOT>& Q = S.gi;
+    double m[RPW][CS];
+    double lam[CS];
+    int q = NS, ybuf = 0;
+    {
+        const double* Jst = S.gi.Hp;
 #pragma unroll
         for (int s = 0; s < CS; ++s) {
-            const int j = lane + 32 * s;
-            if (i < nV && j <= i) S.gi.Hp[D::hp(i, j)] = (i >= nU) ? (i == j ? P.flat_eps : 0.0) : m[r][s];
-        }
-    }
-    if (a.dbg_H) {
-        double* gH = a.dbg_H + (size_t)b * nV * nV;
+            const int jj = lane + 32 * s, j = jj - NS;
+            const int sj = (j >= 0) ? j / NU : 0;
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            const int i = row0 + r;
+            for (int r = 0; r < RPW; ++r) {
+                const int i = row0 + r;
+                double v = 0.0;
+                if (jj < NS) v = (i == nU + jj) ? 1.0 : 0.0;
+                else if (jj < nV && i < nU) {
+                    const int si = i / NU, ci = i - si * NU;
+                    if (si >= sj) {                 // raw row entries of the column pair (sj, .) times Lambda_sj^(-T/2)/sqrt 2
+                        const int cj = j - sj * NU;
+                        const double* jr = Jst + ci * D::NPK + D::pk(si, sj * NU);
+                        v = 0.0;
 #pragma unroll
-            for (int s = 0; s < CS; ++s) {
-                const int j = lane + 32 * s;
-                if (i < nV && j < nV) gH[(size_t)j * nV + i] = (i < nU && j < nU) ? m[r][s] : 0.0;
+                        for (int r2 = 0; r2 < NU; ++r2) v = fma(jr[r2], S.Wi[sj * NU * NU + r2 * NU + cj], v);
+                    }
+                }
+                m[r][s] = v;
             }
+            lam[s] = (jj < NS) ? fabs(S.gi.g[nU + jj]) : 0.0;
         }
     }
-    __syncthreads();
+    __syncthreads();           // staging consumed: the region becomes the packed H
+    // generate_qp.m:29  H = 2 (B' Qbar B + Rbar), packed lower triangle for the symv's (drops, refresh,
+    // objective).  Entry (i, j), i >= j, i the later control at step si:
+    //   H_ij = 2 G_si[c_i] . x^(j)_{si+1}  (+ 2 R on the diagonal)
+    // x^(j)_{si+1} = column j of B_bar at step si: packed rows for the real states, exactly dt for the
+    // integrator state its control drives.  The slack diagonal gets flat_eps.
+    {
+        static_assert(C::real_state(0) == 0 && C::real_state(C::NREAL - 1) == C::NREAL - 1, "real states come first");
+        double* gH = a.dbg_H ? a.dbg_H + (size_t)b * nV * nV : nullptr;
+        for (int e = tid; e < nV * nV; e += NT) {
+            const int i = e / nV, j = e - i * nV;
+            if (j > i) continue;
+            double h = 0.0;
+            if (i < nU) {
+                const int si = i / NU, ci = i - si * NU, cj = j % NU;
+                const double* Gr = S.Gs + (si * NU + ci) * NX;
+                double acc = 0.0;
+#pragma unroll
+                for (int ii = 0; ii < C::NREAL; ++ii) acc = fma(Gr[ii], S.Bf[ii * D::NPK + D::pk(si, j)], acc);
+#pragma unroll
+                for (int ii = 0; ii < C::NINT; ++ii)
+                    if (C::int_ucol(ii) == cj) acc = fma(Gr[C::int_state(ii)], dt, acc);
+                h = 2.0 * acc;
+                if (i == j) h += 2.0 * P.R[ci];
+            }
+            if (gH) { gH[(size_t)j * nV + i] = h; gH[(size_t)i * nV + j] = h; }
+            S.gi.Hp[D::hp(i, j)] = (i >= nU) ? (i == j ? P.flat_eps : 0.0) : h;
+        }
+    }
     if (a.dbg_g) {
         double* gg = a.dbg_g + (size_t)b * nV;
         for (int t = tid; t < nV; t += NT) gg[t] = S.gi.g[t];
     }
-
     STAGE(4);
-    // ---------------------------------------------------------------- factor, lay out, solve
-    using Ops = GiOps<G, GiSm<G, D::NSLOT>>;
-    GiSm<G, D::NSLOT>& Q = S.gi;
-    double lam[CS];
-    int q = 0, ybuf = 0;
-    Ops::factor_and_layout(Q, m, lam, q, nU, NS, nV);     // H_uu -> J = L^-T in registers; slack bounds active
     if (tid < NS) {
         Q.act[tid] = (nU + tid) * 2;                       // slack lower bounds in the working set,
         Q.status[nU + tid] = -1;                           // multiplier R_soft (dual feasible start)

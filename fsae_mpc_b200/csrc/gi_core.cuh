@@ -33,7 +33,11 @@ __device__ unsigned long long g_phase_cycles[16];
 __device__ unsigned long long g_stage_cycles[16];
 #define STAGE_DECL long long sg_t_ = clock64()
 #define STAGE(i) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_stage_cycles[i], (unsigned long long)(n_ - sg_t_)); sg_t_ = n_; } } while (0)
+#define RSTAGE_DECL long long rs_t_ = clock64()
+#define RSTAGE(i) do { if (lane == 0) { const long long n_ = clock64(); atomicAdd(&g_stage_cycles[9 + (i)], (unsigned long long)(n_ - rs_t_)); rs_t_ = n_; } } while (0)
 #else
+#define RSTAGE_DECL
+#define RSTAGE(i)
 #define STAGE_DECL
 #define STAGE(i)
 #define PHASE_DECL
@@ -242,11 +246,18 @@ struct GiOps {
                 const int j = lane + 32 * s;
                 lj[s] = (j > k && j < nC) ? S.colk[buf][j] * rp : 0.0;     // symmetric: W[k][j] = W[j][k]
             }
+            // column slots that lie entirely at or left of the pivot have lj = 0: skipped (warp-uniform)
+            const int s0 = (k + 1) >> 5;                // first slot that still has a column right of the pivot
 #pragma unroll
-            for (int r = 0; r < RPW; ++r) {
-                const double vr = S.colk[buf][row0 + r];
+            for (int sb = 0; sb < CS; ++sb) {
+                if (s0 == sb) {
 #pragma unroll
-                for (int s = 0; s < CS; ++s) m[r][s] = fma(-vr, lj[s], m[r][s]);
+                    for (int r = 0; r < RPW; ++r) {
+                        const double vr = S.colk[buf][row0 + r];
+#pragma unroll
+                        for (int s = sb; s < CS; ++s) m[r][s] = fma(-vr, lj[s], m[r][s]);
+                    }
+                }
             }
             const int kr = k - row0;                    // warp-uniform: does this warp own the pivot row?
             if (kr >= 0 && kr < RPW) {

@@ -46,3 +46,4 @@ stot = sum(sg[i] for i in range(9))
 print(f"kernel stages, cycles per QP (tid 0): total {stot/B:.0f}")
 for i, n in enumerate(snames):
     print(f"  {n:34s} {sg[i]/B:9.0f} cyc  {100*sg[i]/stot:5.1f}%")
+print("recursion warp phases (cycles per QP): " + ", ".join(f"ph{i+1} {sg[9+i]/B:.0f}" for i in range(4)))
