@@ -461,7 +461,8 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
                      : kv == 26 ? launch_fused_v2<KinModel, 40, 2, 6, 1>(ctx, a, st)
                      : kv == 27 ? launch_fused_v2<KinModel, 40, 2, 6, 2>(ctx, a, st)
                      : kv == 28 ? launch_fused_v2<KinModel, 40, 2, 6, 3>(ctx, a, st)
-                     : launch_fused_v2<KinModel, 40, 2, 6, 1>(ctx, a, st);
+                     : kv == 33 ? launch_fused_v2<KinModel, 40, 2, 6, 4>(ctx, a, st)
+                     : launch_fused_v2<KinModel, 40, 2, 6, 2>(ctx, a, st);
         else if (N == 20) rc = v1 ? launch_fused_v1<KinModel, 20, 256>(ctx, a, st) : launch_fused_v2<KinModel, 20, 2>(ctx, a, st);
         else if (N == 80) rc = launch_fused_long<KinModel, 80>(ctx, a, st);
         else ctx->err = "kinematic fused step: horizon must be 20, 40 or 80";

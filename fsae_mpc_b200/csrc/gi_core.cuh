@@ -100,7 +100,7 @@ template <int NVMAX, int NW_ = 8, int KB_ = 1>
 struct GiCfg {
     static constexpr int NW = NW_, NT = 32 * NW_;
     static constexpr int KB = KB_;                           // constraints projected per search (block size)
-    static constexpr int YB = KB_ > 2 ? KB_ : 2;             // ypart buffers
+    static constexpr int YB = 2;                             // ypart buffers (double-buffered)
     static_assert(KB_ >= 1 && NW_ * KB_ <= 32, "block selection reduces NW*KB candidates in one warp");
     static constexpr int RPW = (NVMAX + NW - 1) / NW;      // rows per warp
     static constexpr int RP = RPW * NW;                      // padded rows
@@ -124,6 +124,7 @@ struct GiSm {
     double rowv[G::RP];                // per-warp row vector scratch (gradient / H k)
     double nvec[G::KB][G::RP];         // per-warp rows of the normals of the block's constraints
     double zrow[G::RP];                // per-warp reduced z
+    double xs0[G::RP];                 // x as the block's search saw it (own rows per warp)
     double wpart[3][G::RP];            // symv partials
     double dvec[G::RP];                // LDL' pivots
     double red_val[2][G::NW];
@@ -330,54 +331,18 @@ struct GiOps {
         __syncthreads();                           // x complete
     }
 
-    // y_c = M' n_c for the nc <= KB normals in S.nvec (per-warp rows): ONE pass over the tiles and ONE
-    // barrier for the whole block; identical results in every warp.
-    __device__ __forceinline__ static void matvec_T_multi(SM& S, const double (&m)[RPW][CS], int nc,
-                                                          double (&y)[G::KB][CS]) {
-        constexpr int KB = G::KB;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row0 = warp * RPW;
-#pragma unroll
-        for (int c = 0; c < KB; ++c) {
-            if (c < nc) {
-                double yp[CS];
-#pragma unroll
-                for (int s = 0; s < CS; ++s) yp[s] = 0.0;
-#pragma unroll
-                for (int r = 0; r < RPW; ++r) {
-                    const double v = S.nvec[c][row0 + r];
-#pragma unroll
-                    for (int s = 0; s < CS; ++s) yp[s] = fma(m[r][s], v, yp[s]);
-                }
-#pragma unroll
-                for (int s = 0; s < CS; ++s) S.ypart[c][warp][lane + 32 * s] = yp[s];
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < KB; ++c) {
-#pragma unroll
-            for (int s = 0; s < CS; ++s) {
-                double acc = 0.0;
-                if (c < nc) {
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) acc += S.ypart[c][w][lane + 32 * s];
-                }
-                y[c][s] = acc;
-            }
-        }
-    }
-
     // The dual active-set loop.  On entry: M, lam, q consistent with S.act/S.status, S.x the
     // minimiser on that working set, barrier passed.  On exit S.x is the solution (barrier passed).
     //
-    // Block selection: one search yields the KB most violated constraint sides; ONE pass over the
-    // register tiles projects all their normals (y_c = M'n_c).  The first goes through the full
-    // Goldfarb-Idnani step (partial steps / drops included); the others "piggy-back": every update
-    // of M is a column operation M <- M T, so their projections follow as y_c <- T'y_c (O(nV) per
-    // lane + one warp reduction) and their violations as s_c += t n_c'z = t (y2 . y2_c).  A
-    // piggy-backed add needs no block barrier at all (z, x rows and tile updates are warp-local).
-    // A piggy-backed candidate that is no longer violated is skipped; one that would need a partial
-    // step ends the block (the next search finds it again).
+    // Block selection: one search yields the KB most violated constraint sides.  The first goes
+    // through the full Goldfarb-Idnani step (partial steps / drops included); the others
+    // "piggy-back" on the same search: their normals are already in shared memory, their
+    // current violation follows from the x the search saw, s_c += n_c'(x - x_search), which rides
+    // on the spare column of the projection pass y = M'n_c, so no second evaluation of the
+    // constraints is needed.  A piggy-backed candidate that is no longer violated is skipped; one
+    // that would need a partial step ends the block (the next search finds it again).  Between
+    // the adds of a block x, z and the tile updates are warp-local: the only block barrier of a
+    // piggy-backed add is the one inside the projection.
     template <class Prob>
     __device__ static GiStats solve(const Prob& prob, SM& S, double (&m)[RPW][CS], double (&lam)[CS], int& q,
                                     int& ybuf, int nV, double tol, int max_iter) {
@@ -450,7 +415,7 @@ struct GiOps {
             for (int c = 0; c < KB; ++c) nleft += (cviol[c] < -tol) ? 1 : 0;
             if (q + nleft > nV) nleft = nV - q > 0 ? nV - q : 1;
 
-            // P2: this warp's entries of the block's normals
+            // P2: this warp's entries of the block's normals; the x the search saw (own rows)
 #pragma unroll
             for (int c = 0; c < KB; ++c) {
                 if (c < nleft) {
@@ -461,20 +426,11 @@ struct GiOps {
                     }
                 }
             }
+            if (KB > 1 && nleft > 1 && lane < RPW) S.xs0[row0 + lane] = S.x[row0 + lane];
             __syncwarp();
             PHASE(3);
 
-            // P3: project the block.  A single variable bound has n = +-e_p, so y is +-(row p of M):
-            // the owning warp publishes its row, nobody multiplies or sums partials.
-            double yq[KB][CS];                      // queue of projections; yq[0] is the current candidate
-            bool fresh = true;                      // yq[0] is valid for the current candidate
-            if (KB == 1 || nleft == 1) {
-                fresh = false;
-            } else {
-                matvec_T_multi(S, m, nleft, yq);
-            }
-            PHASE(4);
-
+            int cidx = 0;                           // which of the block's normals is being added
             int pslot = ccode[0] >> 1, pside = (ccode[0] & 1) ? +1 : -1;
             double sp = cviol[0];                   // n'x - b  (< 0)
             double lam_p = 0.0;
@@ -482,11 +438,11 @@ struct GiOps {
             bool piggy = false, dropped = false, failed = false;
             while (true) {
                 if (++st.iters > max_iter) { st.exitflag = GI_EXIT_MAXITER; failed = true; break; }
-                double y[CS];
-                if (fresh) {
-#pragma unroll
-                    for (int s = 0; s < CS; ++s) y[s] = yq[0][s];
-                } else if (prob.is_unit(pslot)) {
+                // P3: y = M'n.  A variable bound has n = +-e_p, so y is +-(row p of M): the owning warp
+                // publishes its row, nobody multiplies or sums partials.  The spare column carries
+                // n'(x - x_search) for a piggy-backed candidate.
+                double y[CS], dsum = 0.0;
+                if (prob.is_unit(pslot)) {
                     const int pr = pslot - row0;               // warp-uniform
                     if (pr >= 0 && pr < RPW) {
 #pragma unroll
@@ -495,167 +451,164 @@ struct GiOps {
 #pragma unroll
                                 for (int s = 0; s < CS; ++s) S.ypart[ybuf][0][lane + 32 * s] = m[r][s];
                             }
+                        if (KB > 1 && piggy && lane == 31) S.ypart[ybuf][0][G::CP - 1] = S.x[pslot] - S.xs0[pslot];
                     }
                     __syncthreads();
                     const double sgn = pside < 0 ? 1.0 : -1.0;
 #pragma unroll
                     for (int s = 0; s < CS; ++s) y[s] = sgn * S.ypart[ybuf][0][lane + 32 * s];
+                    if (KB > 1 && piggy) {
+                        dsum = __shfl_sync(0xffffffffu, y[CS - 1], 31);
+                        if (lane == 31) y[CS - 1] = 0.0;
+                    }
                     ybuf ^= 1;
                 } else {
-                    double dummy;
-                    matvec_T(S, m, ybuf, S.nvec[0], 0.0, y, dummy);
-                }
-                fresh = false;
-                PHASE(5);
-                // P4 (every warp, redundantly): step lengths
-                double d2 = 0.0, t1 = INFINITY;
-                int l = -1;
-#pragma unroll
-                for (int s = 0; s < CS; ++s) {      // branch-free: every lane does the same work
-                    const int j = lane + 32 * s;
-                    const double yy = y[s];
-                    const bool isJ = (j >= q) & (j < nV);
-                    const bool cand = (j < q) & (yy > 1e-13);
-                    d2 = fma(isJ ? yy : 0.0, yy, d2);
-                    const double tj = cand ? lam[s] * __drcp_rn(cand ? yy : 1.0) : INFINITY;
-                    const bool better = tj < t1;
-                    t1 = better ? tj : t1;
-                    l = better ? j : l;
-                }
-                d2 = warp_sum_d(d2);
-                {
-                    unsigned long long km;
-                    const int wl = warp_argmin_key(dkey(t1), km);
-                    l = __shfl_sync(0xffffffffu, l, wl);
-                    t1 = dkey_inv(km);
-                }
-                const bool lin_dep = !(d2 > 1e-13 * fmax(1.0, nn));
-                const double inv_d2 = __drcp_rn(d2);
-                const double t2 = lin_dep ? INFINITY : (sp < 0.0 ? -sp * inv_d2 : 0.0);
-                const bool full = (t2 <= t1);
-                if (piggy && !full) { --st.iters; PHASE_COUNT(14); break; }          // left to the next search
-                if (isinf(t1) && isinf(t2)) { st.exitflag = GI_EXIT_INFEASIBLE; failed = true; break; }
-                const bool primal = !isinf(t2);
-                const double t = full ? t2 : t1;
-                PHASE(6);
-                // P5: z = J2 y2, x += t z  (this warp's rows only)
-                if (primal) {
-                    matvec_N(S, m, y, q, nV);
-                    if (lane < RPW) {
-                        const int i = row0 + lane;
-                        if (i < nV) S.x[i] += t * S.zrow[i];
+                    double extra = 0.0;
+                    if (KB > 1 && piggy) {
+                        if (lane < RPW) extra = S.nvec[cidx][row0 + lane] * (S.x[row0 + lane] - S.xs0[row0 + lane]);
+                        extra = warp_sum_d(extra);
                     }
-                    sp += t * d2;
+                    matvec_T(S, m, ybuf, S.nvec[cidx], extra, y, dsum);
                 }
-                if (full && tid == 0) {
-                    // bookkeeping of the add; published by the barrier that ends the block
-                    S.act[q] = pslot * 2 + (pside > 0 ? 1 : 0);
-                    S.status[pslot] = (int8_t)pside;
+                PHASE(5);
+                bool more = true;                   // (piggy-backed only) keep going with this candidate
+                if (KB > 1 && piggy) {
+                    sp = cviol[0] + dsum;
+                    if (!(sp < -tol)) { more = false; PHASE_COUNT(15); }
                 }
+                double d2 = 0.0, t1 = INFINITY, inv_d2 = 0.0, t = 0.0;
+                int l = -1;
+                bool full = false, primal = false;
+                if (more) {
+                    // P4 (every warp, redundantly): step lengths
 #pragma unroll
-                for (int s = 0; s < CS; ++s) {
-                    const int j = lane + 32 * s;
-                    if (j < q) lam[s] -= t * y[s];
+                    for (int s = 0; s < CS; ++s) {      // branch-free: every lane does the same work
+                        const int j = lane + 32 * s;
+                        const double yy = y[s];
+                        const bool isJ = (j >= q) & (j < nV);
+                        const bool cand = (j < q) & (yy > 1e-13);
+                        d2 = fma(isJ ? yy : 0.0, yy, d2);
+                        const double tj = cand ? lam[s] * __drcp_rn(cand ? yy : 1.0) : INFINITY;
+                        const bool better = tj < t1;
+                        t1 = better ? tj : t1;
+                        l = better ? j : l;
+                    }
+                    d2 = warp_sum_d(d2);
+                    {
+                        unsigned long long km;
+                        const int wl = warp_argmin_key(dkey(t1), km);
+                        l = __shfl_sync(0xffffffffu, l, wl);
+                        t1 = dkey_inv(km);
+                    }
+                    const bool lin_dep = !(d2 > 1e-13 * fmax(1.0, nn));
+                    inv_d2 = __drcp_rn(d2);
+                    const double t2 = lin_dep ? INFINITY : (sp < 0.0 ? -sp * inv_d2 : 0.0);
+                    full = (t2 <= t1);
+                    if (piggy && !full) { --st.iters; PHASE_COUNT(14); break; }     // left to the next search
+                    if (isinf(t1) && isinf(t2)) { st.exitflag = GI_EXIT_INFEASIBLE; failed = true; break; }
+                    primal = !isinf(t2);
+                    t = full ? t2 : t1;
+                    PHASE(6);
+                    // P5: z = J2 y2, x += t z  (this warp's rows only)
+                    if (primal) {
+                        matvec_N(S, m, y, q, nV);
+                        if (lane < RPW) {
+                            const int i = row0 + lane;
+                            if (i < nV) S.x[i] += t * S.zrow[i];
+                        }
+                        sp += t * d2;
+                    }
+                    if (full && tid == 0) {
+                        // bookkeeping of the add; published by the barrier that ends the block
+                        S.act[q] = pslot * 2 + (pside > 0 ? 1 : 0);
+                        S.status[pslot] = (int8_t)pside;
+                    }
+#pragma unroll
+                    for (int s = 0; s < CS; ++s) {
+                        const int j = lane + 32 * s;
+                        if (j < q) lam[s] -= t * y[s];
+                    }
+                    lam_p += t;
+                    PHASE(7);
+                } else {
+                    --st.iters;
                 }
-                lam_p += t;
-                PHASE(7);
-                if (full) {
-                    // P6a: add p.  K1 <- K1 - k r', J2 <- J2 (I - beta v v'), column q <- k = z/d2
-                    const int qs = q >> 5, ql = q & 31;
-                    if (lane == ql) {
+                if (!more || full) {
+                    if (more) {
+                        // P6a: add p.  K1 <- K1 - k r', J2 <- J2 (I - beta v v'), column q <- k = z/d2
+                        const int qs = q >> 5, ql = q & 31;
+                        if (lane == ql) {
+#pragma unroll
+                            for (int s = 0; s < CS; ++s)
+                                if (s == qs) {
+#pragma unroll
+                                    for (int r = 0; r < RPW; ++r) S.colk[0][row0 + r] = m[r][s];
+                                }
+                        }
+                        __syncwarp();
+                        const double delta = d2 * rsqrt(d2);
+                        double yq_l = 0.0;
 #pragma unroll
                         for (int s = 0; s < CS; ++s)
+                            if (s == qs) yq_l = y[s];
+                        const double yqv = __shfl_sync(0xffffffffu, yq_l, ql);
+                        const double sgd = (yqv >= 0.0) ? delta : -delta;
+                        const double beta = __drcp_rn(d2 + fabs(yqv) * delta);
+                        // Column slots entirely left of q take  m - kr y,  slots entirely right of it
+                        // m - wr y  (one FMA per element, warp-uniform choice); only the slot that holds
+                        // column q mixes the three cases:  c*m - kr*ya - wr*yb  with (c, ya, yb) =
+                        // (1, y, 0) for j < q, (0, -1, 0) for j == q, (1, 0, y) for j > q.
+                        double ccq = 1.0, yaq = 0.0, ybq = 0.0;
+#pragma unroll
+                        for (int s = 0; s < CS; ++s) {
                             if (s == qs) {
-#pragma unroll
-                                for (int r = 0; r < RPW; ++r) S.colk[0][row0 + r] = m[r][s];
-                            }
-                    }
-                    __syncwarp();
-                    const double delta = d2 * rsqrt(d2);
-                    double yq_l = 0.0;
-#pragma unroll
-                    for (int s = 0; s < CS; ++s)
-                        if (s == qs) yq_l = y[s];
-                    const double yqv = __shfl_sync(0xffffffffu, yq_l, ql);
-                    const double sgd = (yqv >= 0.0) ? delta : -delta;
-                    const double beta = __drcp_rn(d2 + fabs(yqv) * delta);
-                    // new = c*cur - kr*ya - wr*yb with (c, ya, yb) = (1, y, 0) for j < q,
-                    // (0, -1, 0) for j == q, (1, 0, y) for j > q: no per-element selects
-                    double cc[CS], ya[CS], yb[CS];
-#pragma unroll
-                    for (int s = 0; s < CS; ++s) {
-                        const int j = lane + 32 * s;
-                        cc[s] = (j == q) ? 0.0 : 1.0;
-                        ya[s] = (j < q) ? y[s] : (j == q ? -1.0 : 0.0);
-                        yb[s] = (j > q) ? y[s] : 0.0;
-                    }
-#pragma unroll
-                    for (int r = 0; r < RPW; ++r) {
-                        const double zr = S.zrow[row0 + r];
-                        const double kr = zr * inv_d2;
-                        const double wr = (zr + sgd * S.colk[0][row0 + r]) * beta;
-#pragma unroll
-                        for (int s = 0; s < CS; ++s) m[r][s] = fma(-wr, yb[s], fma(-kr, ya[s], cc[s] * m[r][s]));
-                    }
-#pragma unroll
-                    for (int s = 0; s < CS; ++s) {
-                        const int j = lane + 32 * s;
-                        if (j == q) lam[s] = lam_p;
-                    }
-                    ++st.n_add;
-                    __syncwarp();
-                    PHASE(8);
-                    if (KB == 1 || dropped || nleft <= 1) { ++q; break; }
-                    // the column operation applied to the projections still queued:
-                    //   j < q : y_j - kappa y_j^p,  j = q : kappa,  j > q : y_j - omega y_j^p
-                    //   kappa = (y2 . y2^p)/d2,  omega = beta (y2 . y2^p + sgd y_q);  s += t (y2 . y2^p)
-#pragma unroll
-                    for (int c = 1; c < KB; ++c) {
-                        if (c < nleft) {
-                            double part = 0.0, yc_q = 0.0;
-#pragma unroll
-                            for (int s = 0; s < CS; ++s) {
                                 const int j = lane + 32 * s;
-                                part = fma((j >= q && j < nV) ? y[s] : 0.0, yq[c][s], part);
-                                if (s == qs) yc_q = yq[c][s];
+                                ccq = (j == q) ? 0.0 : 1.0;
+                                yaq = (j < q) ? y[s] : (j == q ? -1.0 : 0.0);
+                                ybq = (j > q) ? y[s] : 0.0;
                             }
-                            const double c12 = warp_sum_d(part);
-                            yc_q = __shfl_sync(0xffffffffu, yc_q, ql);
-                            const double kappa = c12 * inv_d2;
-                            const double omega = beta * (c12 + sgd * yc_q);
+                        }
 #pragma unroll
-                            for (int s = 0; s < CS; ++s) {
-                                const int j = lane + 32 * s;
-                                const double co = (j < q) ? kappa : omega;
-                                const double v = fma(-co, y[s], yq[c][s]);
-                                yq[c][s] = (j == q) ? kappa : v;
+                        for (int qq = 0; qq < CS; ++qq) {
+                            if (qs == qq) {                 // one specialised copy per position of the mixed slot
+#pragma unroll
+                                for (int r = 0; r < RPW; ++r) {
+                                    const double zr = S.zrow[row0 + r];
+                                    const double kr = zr * inv_d2;
+                                    const double wr = (zr + sgd * S.colk[0][row0 + r]) * beta;
+#pragma unroll
+                                    for (int s = 0; s < CS; ++s) {
+                                        if (s < qq) m[r][s] = fma(-kr, y[s], m[r][s]);
+                                        else if (s > qq) m[r][s] = fma(-wr, y[s], m[r][s]);
+                                        else m[r][s] = fma(-wr, ybq, fma(-kr, yaq, ccq * m[r][s]));
+                                    }
+                                }
                             }
-                            cviol[c] += t * c12;
                         }
-                    }
-                    ++q;
-                    // next candidate that is still violated
-                    bool more = false;
-                    while (nleft > 1) {
 #pragma unroll
-                        for (int c = 0; c + 1 < KB; ++c) {
-                            cviol[c] = cviol[c + 1];
-                            ccode[c] = ccode[c + 1];
-#pragma unroll
-                            for (int s = 0; s < CS; ++s) yq[c][s] = yq[c + 1][s];
+                        for (int s = 0; s < CS; ++s) {
+                            const int j = lane + 32 * s;
+                            if (j == q) lam[s] = lam_p;
                         }
-                        --nleft;
-                        if (cviol[0] < -tol) { more = true; break; }
-                        PHASE_COUNT(15);
+                        ++q;
+                        ++st.n_add;
+                        __syncwarp();
+                        PHASE(8);
                     }
-                    if (!more || q >= nV) break;
+                    // next candidate of the block
+                    if (KB == 1 || dropped || nleft <= 1 || q >= nV) break;
+#pragma unroll
+                    for (int c = 0; c + 1 < KB; ++c) {
+                        cviol[c] = cviol[c + 1];
+                        ccode[c] = ccode[c + 1];
+                    }
+                    --nleft;
+                    ++cidx;
                     pslot = ccode[0] >> 1;
                     pside = (ccode[0] & 1) ? +1 : -1;
-                    sp = cviol[0];
                     lam_p = 0.0;
                     nn = prob.norm2(pslot);
                     piggy = true;
-                    fresh = true;
                     PHASE_COUNT(13);
                     PHASE(9);
                     continue;

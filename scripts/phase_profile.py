@@ -32,8 +32,8 @@ lib.fsae_profile_read_stages(mpc._ctx, sg, 1)
 r = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, 0.05, xl, ul)
 lib.fsae_profile_read(mpc._ctx, out, 1)
 adds, drops, refr = mpc.counters()
-names = ["loop/refresh/end-of-block barrier", "P1 search (policy)", "P1 top-KB argmin+barrier", "P2 normals", "P3 block projection Y=M'N (+barrier)",
-         "P3' y from queue / re-projection", "P4 step lengths", "P5 z=J2y2, x update", "P6a add update", "queue transform + advance", "P6b drop"]
+names = ["loop/refresh/end-of-block barrier", "P1 search (policy)", "P1 top-KB argmin+barrier", "P2 normals", "(unused)",
+         "P3 y=M'n (+barrier)", "P4 step lengths", "P5 z=J2y2, x update", "P6a add update", "queue transform + advance", "P6b drop"]
 tot = sum(out[i] for i in range(11))
 print(f"searches/QP {out[12]/B:.1f}  piggy-backed adds/QP {out[13]/B:.1f}  piggy aborts (partial step)/QP {out[14]/B:.2f}  skipped (no longer violated)/QP {out[15]/B:.2f}")
 it = r.iters.sum()
