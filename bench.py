@@ -33,17 +33,25 @@ N_STEPS = 40
 def algorithmic_flops(adds, drops, refreshes, n_qp, nV=81, nU=80, N=40, q_mean=None):
     """FP64 flops the solve path NEEDS (FMA = 2), from the active-set event counts the kernel
     reports (DESIGN.md 'Algorithmic work').  Per QP:
-       setup   = B_bar chains + H build + LDL'/inverse + initial point
+       setup   = B_bar chains + Gramian/Riccati recursions + adjoint rows of J + tile fill
+                 + packed H + g + row norms + initial point      (no dense factorisation)
        add     = M'n (nV^2) + J2 y (nV (nV-q)) + rank-1 update (nV^2) + constraint evaluation
        drop    = H k (nV^2) + K1'w (nV q) + K1 update (nV q) + re-projection M'n (nV^2)
        refresh = H x (nV^2) + M'grad (nV^2) + J2 y (nV (nV-q))
     """
+    NX, NU, NREAL = 5, 2, 3
     if q_mean is None:
         q_mean = max(1.0, 0.5 * (adds - drops) / max(n_qp, 1))
     cons_eval = nU * (N + 1) / 2 * 2 + 2 * N * (N + 1) / 2          # packed n-rows + 2 prefix sums
-    setup = (nU * (N + 1) / 2 * 3 * 5                                 # B_bar chains (3 real rows x 5)
-             + 6.0 * sum((i + 1) * (N - i // 2) for i in range(nU))  # H: 3 rows x 2 FMA per (pair,k)
-             + nU ** 3 / 3.0                                          # LDL' + triangular inverse
+    per_stage = (2 * NX * NX * NREAL + 2 * NU * NX * NX               # W A, P A, B'P, B'W
+                 + NU * NX * NREAL + 3 * NX + 2 * NU * NX             # S, Lambda, K
+                 + 2 * NX * NX * NREAL + NX * NX * NU)                # W', P'
+    setup = (nU * (N + 1) / 2 * NREAL * NX                            # B_bar chains
+             + N * per_stage                                          # Gramian + Riccati recursions
+             + NU * (N * (N - 1) / 2) * (NU * NX + NX * (NREAL + NU)) # adjoint rows of J
+             + 2 * nU * (nU + 2) / 4 * 2                              # tile fill (x Lambda^(-T/2))
+             + nU * (nU + 1) / 2 * (NREAL + 1)                        # packed H, one dot product per entry
+             + nU * (N + 1) / 2 * (NREAL + 1) + nU * (N + 1) / 2 * 2  # g; per-step Gram / column sums
              + 2 * nV * nV)                                           # x0 = -J J' g
     add = 2 * nV * nV + nV * (nV - q_mean) + cons_eval
     drop = 2 * nV * nV + 2 * nV * q_mean

@@ -448,21 +448,14 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
     int rc = FSAE_ERR_UNSUPPORTED;
     if (model == FSAE_MODEL_KINEMATIC) {
         const bool v1 = ctx->kernel_version == 1;
-        const int kv = ctx->kernel_version;      // 2x: block size x (tuning/cross-check switch)
+        // tuning / cross-check switch (fsae_debug_set_kernel_version): warp count x block size variants
+        const int kv = ctx->kernel_version;
         if (N == 40) rc = v1 ? launch_fused_v1<KinModel, 40, 256>(ctx, a, st)
-                     : kv == 21 ? launch_fused_v2<KinModel, 40, 2, 8, 1>(ctx, a, st)
-                     : kv == 22 ? launch_fused_v2<KinModel, 40, 2, 8, 2>(ctx, a, st)
-                     : kv == 23 ? launch_fused_v2<KinModel, 40, 2, 8, 3>(ctx, a, st)
-                     : kv == 25 ? launch_fused_v2<KinModel, 40, 2, 5, 1>(ctx, a, st)
-                     : kv == 29 ? launch_fused_v2<KinModel, 40, 2, 4, 1>(ctx, a, st)
-                     : kv == 30 ? launch_fused_v2<KinModel, 40, 2, 4, 2>(ctx, a, st)
-                     : kv == 31 ? launch_fused_v2<KinModel, 40, 2, 4, 3>(ctx, a, st)
-                     : kv == 32 ? launch_fused_v2<KinModel, 40, 2, 4, 4>(ctx, a, st)
-                     : kv == 26 ? launch_fused_v2<KinModel, 40, 2, 6, 1>(ctx, a, st)
-                     : kv == 27 ? launch_fused_v2<KinModel, 40, 2, 6, 2>(ctx, a, st)
-                     : kv == 28 ? launch_fused_v2<KinModel, 40, 2, 6, 3>(ctx, a, st)
-                     : kv == 33 ? launch_fused_v2<KinModel, 40, 2, 6, 4>(ctx, a, st)
-                     : launch_fused_v2<KinModel, 40, 2, 6, 2>(ctx, a, st);
+                     : kv == 21 ? launch_fused_v2<KinModel, 40, 1, 8, 1>(ctx, a, st)     // 8 warps (1 CTA/SM: shared memory)
+                     : kv == 26 ? launch_fused_v2<KinModel, 40, 2, 6, 1>(ctx, a, st)     // 6 warps, one constraint per search
+                     : kv == 28 ? launch_fused_v2<KinModel, 40, 2, 6, 3>(ctx, a, st)     // 6 warps, blocks of 3
+                     : kv == 29 ? launch_fused_v2<KinModel, 40, 2, 4, 1>(ctx, a, st)     // 4 warps
+                     : launch_fused_v2<KinModel, 40, 2, 6, 2>(ctx, a, st);               // product: 6 warps, blocks of 2
         else if (N == 20) rc = v1 ? launch_fused_v1<KinModel, 20, 256>(ctx, a, st) : launch_fused_v2<KinModel, 20, 2>(ctx, a, st);
         else if (N == 80) rc = launch_fused_long<KinModel, 80>(ctx, a, st);
         else ctx->err = "kinematic fused step: horizon must be 20, 40 or 80";
@@ -781,7 +774,7 @@ extern "C" int fsae_probe_fp64_tflops(fsae_ctx* ctx, double* tflops) {
 
 // select the fused kernel variant (tests cross-check v1 against v2); returns the previous one
 extern "C" int fsae_debug_set_kernel_version(fsae_ctx* ctx, int v) {
-    if (!ctx || (v != 1 && v != 2 && (v < 21 || v > 39))) return FSAE_ERR_ARG;
+    if (!ctx || (v != 1 && v != 2 && v != 21 && v != 26 && v != 28 && v != 29)) return FSAE_ERR_ARG;
     const int old = ctx->kernel_version;
     ctx->kernel_version = v;
     return old;

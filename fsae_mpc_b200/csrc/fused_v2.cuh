@@ -43,7 +43,7 @@ struct SmemV2 {
     double cg[C::NCG];
     double rlo[D::NROWS], rup[D::NROWS];
     double rn2[D::NROWS];              // squared norm of each row's normal (linear-dependence test)
-    static constexpr bool ROWNORMS = D::NROWS <= 256;  // larger row sets use 1 as the scale
+    static constexpr bool ROWNORMS = true;             // closed form (below): cheap for every model
     static constexpr int NGR = C::NCR * (C::NCR + 1) / 2;
     double gram[ROWNORMS ? N * NGR : 1];            // per step: Gram matrix of the constraint B_bar rows
     double csum[ROWNORMS ? N * C::NCR * D::NU : 1]; // per step: their sums over each control's columns

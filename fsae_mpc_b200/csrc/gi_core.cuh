@@ -349,8 +349,72 @@ struct GiOps {
         constexpr int KB = G::KB;
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row0 = warp * RPW;
         GiStats st = {0, GI_EXIT_SOLVED, 0, 0, 0};
-        int rbuf = 0;
+        int rbuf = 0, drops_at_refresh = 0;
         PHASE_DECL;
+        // drop working-set column l: K1 <- K1 + k r'^T with r' = -K1' H k / k'Hk (k = column l), the freed
+        // direction k / sqrt(k'Hk) joins J2 as column q-1, column q-1 of K1 moves into slot l
+        auto drop_column = [&](int l) {
+            const int ls = l >> 5, ll = l & 31;
+            if (lane == ll) {
+#pragma unroll
+                for (int s = 0; s < CS; ++s)
+                    if (s == ls) {
+#pragma unroll
+                        for (int r = 0; r < RPW; ++r) S.colk[1][row0 + r] = m[r][s];
+                    }
+            }
+            __syncthreads();                                 // k = M[:, l] visible block-wide
+            symv_to_rowv(S, S.colk[1], nullptr, nV);         // rowv = H k   (barrier inside)
+            double kw = 0.0;
+            if (lane < RPW && row0 + lane < nV) kw = S.colk[1][row0 + lane] * S.rowv[row0 + lane];
+            kw = warp_sum_d(kw);
+            double rp[CS], kHk;
+            matvec_T(S, m, ybuf, S.rowv, kw, rp, kHk);       // rp_j = M[:,j]' (H k), kHk piggy-backed
+            const double ik = 1.0 / kHk;
+            const double rs = rsqrt(kHk);
+            const int q1 = q - 1, q1s = q1 >> 5, q1l = q1 & 31;
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                const double kr = S.colk[1][row0 + r];
+#pragma unroll
+                for (int s = 0; s < CS; ++s) {
+                    const int j = lane + 32 * s;
+                    if (j < q && j != l) m[r][s] -= kr * (rp[s] * ik);
+                }
+                double last = 0.0;
+#pragma unroll
+                for (int s = 0; s < CS; ++s)
+                    if (s == q1s) last = m[r][s];
+                last = __shfl_sync(0xffffffffu, last, q1l);
+#pragma unroll
+                for (int s = 0; s < CS; ++s) {
+                    const int j = lane + 32 * s;
+                    if (j == l && l != q1) m[r][s] = last;
+                }
+#pragma unroll
+                for (int s = 0; s < CS; ++s) {
+                    const int j = lane + 32 * s;
+                    if (j == q1) m[r][s] = kr * rs;
+                }
+            }
+            double lam_last = 0.0;
+#pragma unroll
+            for (int s = 0; s < CS; ++s)
+                if (s == q1s) lam_last = lam[s];
+            lam_last = __shfl_sync(0xffffffffu, lam_last, q1l);
+#pragma unroll
+            for (int s = 0; s < CS; ++s) {
+                const int j = lane + 32 * s;
+                if (j == l && l != q1) lam[s] = lam_last;
+                if (j == q1) lam[s] = 0.0;
+            }
+            if (tid == 0) {
+                S.status[S.act[l] >> 1] = 0;
+                S.act[l] = S.act[q1];
+            }
+            --q;
+            ++st.n_drop;
+        };
         while (true) {
             // P1: the KB most violated inactive constraint sides (policy evaluates its slots; one
             // candidate per thread)
@@ -391,23 +455,48 @@ struct GiOps {
             if (!(cviol[0] < -tol)) {
                 // the refresh repairs what chains of partial steps leave behind; a run of pure
                 // full steps keeps x the exact working-set minimiser (to round-off)
-                if (st.n_refresh >= 1 || st.n_drop == 0) break;
+                if (st.n_drop == drops_at_refresh) break;
                 // refresh: Newton step on the active manifold + multipliers from stationarity
+                // (again whenever further partial steps followed the previous refresh)
                 ++st.n_refresh;
-                symv_to_rowv(S, S.x, S.g, nV);                       // rowv = H x + g
-                double y[CS], dummy;
-                matvec_T(S, m, ybuf, S.rowv, 0.0, y, dummy);
-                matvec_N(S, m, y, q, nV);
-                if (lane < RPW) {
-                    const int i = row0 + lane;
-                    if (i < nV) S.x[i] -= S.zrow[i];
-                }
+                drops_at_refresh = st.n_drop;
+                // Round-off in long chains of partial steps (multipliers of size R_soft ~ 1e8 next to
+                // multipliers of size 1) can leave a constraint in the working set whose true multiplier
+                // is negative.  The multipliers recomputed from stationarity show it: such a column is
+                // dropped and the step repeated (then the loop goes on from a dual-feasible point).
+                for (int pass = 0;; ++pass) {
+                    symv_to_rowv(S, S.x, S.g, nV);                       // rowv = H x + g
+                    double y[CS], dummy;
+                    matvec_T(S, m, ybuf, S.rowv, 0.0, y, dummy);
+                    matvec_N(S, m, y, q, nV);
+                    if (lane < RPW) {
+                        const int i = row0 + lane;
+                        if (i < nV) S.x[i] -= S.zrow[i];
+                    }
+                    double ymin = 0.0, ymax = 0.0;
+                    int lmin = -1;
 #pragma unroll
-                for (int s = 0; s < CS; ++s) {
-                    const int j = lane + 32 * s;
-                    if (j < q) lam[s] = fmax(y[s], 0.0);
+                    for (int s = 0; s < CS; ++s) {
+                        const int j = lane + 32 * s;
+                        if (j < q) {
+                            lam[s] = fmax(y[s], 0.0);
+                            ymax = fmax(ymax, fabs(y[s]));
+                            if (y[s] < ymin) { ymin = y[s]; lmin = j; }
+                        }
+                    }
+                    {
+                        unsigned long long km;
+                        const int wl = warp_argmin_key(dkey(ymin), km);
+                        lmin = __shfl_sync(0xffffffffu, lmin, wl);
+                        ymin = dkey_inv(km);
+                        (void)warp_argmin_key(dkey(-ymax), km);
+                        ymax = -dkey_inv(km);
+                    }
+                    __syncthreads();                   // x complete
+                    if (!(ymin < -1e-10 * (1.0 + ymax)) || pass >= 8 || ++st.iters > max_iter) break;
+                    drop_column(lmin);
+                    drops_at_refresh = st.n_drop;
                 }
-                __syncthreads();                   // x complete
                 continue;
             }
             int nleft = 0;                          // candidates (sorted by violation: a prefix is valid)
@@ -614,70 +703,10 @@ struct GiOps {
                     continue;
                 }
                 // P6b: drop active constraint l (column l of K1)
-                {
-                    dropped = true;
-                    const int ls = l >> 5, ll = l & 31;
-                    if (lane == ll) {
-#pragma unroll
-                        for (int s = 0; s < CS; ++s)
-                            if (s == ls) {
-#pragma unroll
-                                for (int r = 0; r < RPW; ++r) S.colk[1][row0 + r] = m[r][s];
-                            }
-                    }
-                    __syncthreads();                                 // k = M[:, l] visible block-wide
-                    symv_to_rowv(S, S.colk[1], nullptr, nV);         // rowv = H k   (barrier inside)
-                    double kw = 0.0;
-                    if (lane < RPW && row0 + lane < nV) kw = S.colk[1][row0 + lane] * S.rowv[row0 + lane];
-                    kw = warp_sum_d(kw);
-                    double rp[CS], kHk;
-                    matvec_T(S, m, ybuf, S.rowv, kw, rp, kHk);       // rp_j = M[:,j]' (H k), kHk piggy-backed
-                    const double ik = 1.0 / kHk;
-                    const double rs = rsqrt(kHk);
-                    const int q1 = q - 1, q1s = q1 >> 5, q1l = q1 & 31;
-#pragma unroll
-                    for (int r = 0; r < RPW; ++r) {
-                        const double kr = S.colk[1][row0 + r];
-#pragma unroll
-                        for (int s = 0; s < CS; ++s) {
-                            const int j = lane + 32 * s;
-                            if (j < q && j != l) m[r][s] -= kr * (rp[s] * ik);
-                        }
-                        double last = 0.0;
-#pragma unroll
-                        for (int s = 0; s < CS; ++s)
-                            if (s == q1s) last = m[r][s];
-                        last = __shfl_sync(0xffffffffu, last, q1l);
-#pragma unroll
-                        for (int s = 0; s < CS; ++s) {
-                            const int j = lane + 32 * s;
-                            if (j == l && l != q1) m[r][s] = last;
-                        }
-#pragma unroll
-                        for (int s = 0; s < CS; ++s) {
-                            const int j = lane + 32 * s;
-                            if (j == q1) m[r][s] = kr * rs;
-                        }
-                    }
-                    double lam_last = 0.0;
-#pragma unroll
-                    for (int s = 0; s < CS; ++s)
-                        if (s == q1s) lam_last = lam[s];
-                    lam_last = __shfl_sync(0xffffffffu, lam_last, q1l);
-#pragma unroll
-                    for (int s = 0; s < CS; ++s) {
-                        const int j = lane + 32 * s;
-                        if (j == l && l != q1) lam[s] = lam_last;
-                        if (j == q1) lam[s] = 0.0;
-                    }
-                    if (tid == 0) {
-                        S.status[S.act[l] >> 1] = 0;
-                        S.act[l] = S.act[q1];
-                    }
-                    --q;
-                    ++st.n_drop;
-                    PHASE(10);
-                }
+                dropped = true;
+                drop_column(l);
+                PHASE(10);
+
             }
             if (failed) break;
             __syncthreads();                       // x, act, status of the whole block published

@@ -164,6 +164,28 @@ def test_kernel_variants_agree(mpc):
     assert same.mean() > 0.99
 
 
+@pytest.mark.parametrize("kv", [21, 26, 28, 29])
+def test_warp_count_and_block_size_variants_agree(mpc, kv):
+    """The dual active-set core is a template over the warp count (tile geometry) and the number of
+    constraints taken per search (block size).  Every instantiation must reach the same minimiser and
+    the same working set as the product configuration, whatever its pivot order."""
+    from fsae_mpc_b200 import workload as wl
+    x0, xr, xl, ul = wl.perturbed_batch("kinematic", "fsg2019", 1500, seed=11)
+    r2 = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
+    old = mpc.set_kernel_version(kv)
+    try:
+        rv = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
+    finally:
+        mpc.set_kernel_version(old)
+    assert (r2.exitflag == 0).all() and (rv.exitflag == 0).all()
+    scale = np.maximum(1.0, np.abs(r2.u_opt).max(axis=1))
+    assert (np.abs(rv.u_opt - r2.u_opt).max(axis=1) / scale).max() < 1e-8
+    assert np.abs(rv.x_opt - r2.x_opt).max() < 1e-7
+    assert (np.abs(rv.fval - r2.fval) / (1.0 + np.abs(r2.fval))).max() < 1e-10
+    same = (rv.workingSetB == r2.workingSetB).all(axis=1) & (rv.workingSetC == r2.workingSetC).all(axis=1)
+    assert same.mean() > 0.99
+
+
 def test_sqp_passes_match_oracle_loop(mpc, fso):
     """BASELINE configs[3]: repeated relinearise+QP on fso2020, against the oracle iterated the
     same way (x_lin, u_lin <- previous x_opt, u_opt)."""
