@@ -516,7 +516,45 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
     // ---------------------------------------------------------------- Goldfarb-Idnani, K-form
     const double tol = P.feas_tol;
     const int max_iter = P.max_iter > 0 ? P.max_iter : 5 * (nV + C::n_ref_rows(N));
-    unsigned long long n_add = 0, n_drop = 0;
+    unsigned long long n_add = 0, n_drop = 0, drops_at_refresh = 0;
+    // drop working-set column l (all threads; barrier on exit)
+    auto drop_column = [&](int l) {
+        const int q = S.isc[0];
+        for (int i = tid; i < nV; i += NT) S.kv[i] = ldM<MG>(&Mop[i * LD + l]);
+        __syncthreads();
+        symv_packed<D, NT>(S.Hp, S.kv, S.wv);
+        __syncthreads();
+        matvec_T_parts<D, NT, MG>(Mop, S.wv, S.part);     // all columns; only j<q, j!=l used
+        if (warp == 0) {
+            double acc = 0.0;
+            for (int i = lane; i < nV; i += 32) acc += S.kv[i] * S.wv[i];
+            acc = warp_sum(acc);
+            if (lane == 0) S.sc[4] = acc;
+        }
+        __syncthreads();
+        const double kHk = S.sc[4];
+        for (int j = tid; j < q; j += NT)
+            S.z[j] = -(S.part[j] + S.part[nV + j] + S.part[2 * nV + j]) / kHk;   // r'
+        __syncthreads();
+        for (int tt = tid; tt < nV * q; tt += NT) {
+            const int i = tt / q, j = tt - i * q;
+            if (j != l) Mop[i * LD + j] = ldM<MG>(&Mop[i * LD + j]) + S.kv[i] * S.z[j];
+        }
+        __syncthreads();
+        const double rs = rsqrt(kHk);
+        for (int i = tid; i < nV; i += NT) {
+            if (l != q - 1) Mop[i * LD + l] = ldM<MG>(&Mop[i * LD + q - 1]);
+            Mop[i * LD + q - 1] = S.kv[i] * rs;
+        }
+        if (tid == 0) {
+            S.status[S.act[l] >> 1] = 0;
+            S.act[l] = S.act[q - 1];
+            S.lam[l] = S.lam[q - 1];
+            S.isc[0] = q - 1;
+        }
+++n_drop;
+        __syncthreads();
+    };
     while (true) {
         // P1: most violated inactive constraint side
         eval_xs<Model, N, NT, MG>(S, S.x, dt, S.xs);
@@ -550,32 +588,44 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
         int pcode;
         block_argmin<NT>(best, best_i, S.red_val, S.red_idx, viol, pcode);
         if (!(viol < -tol)) {
-            // converged on this working set: one refresh (Newton step on the active manifold,
-            // multipliers from stationarity) removes the round-off that partial steps leave.
-            if (S.isc[7] >= 2) break;
-            const int q = S.isc[0];
-            symv_packed<D, NT>(S.Hp, S.x, S.wv);
-            __syncthreads();
-            for (int i = tid; i < nV; i += NT) S.wv[i] += S.g[i];
-            __syncthreads();
-            matvec_T_parts<D, NT, MG>(Mop, S.wv, S.part);
-            __syncthreads();
-            for (int j = tid; j < nV; j += NT) S.y[j] = S.part[j] + S.part[nV + j] + S.part[2 * nV + j];
-            __syncthreads();
-            matvec_N_parts<D, NT, MG>(Mop, S.y, q, S.part);
-            __syncthreads();
-            double dxm = 0.0;
-            for (int i = tid; i < nV; i += NT) {
-                const double dx = S.part[i] + S.part[nV + i] + S.part[2 * nV + i];
-                S.x[i] -= dx;
-                dxm = fmax(dxm, fabs(dx));
+            // converged on this working set: if partial steps happened since the last refresh, a
+            // Newton step on the active manifold removes the round-off they leave and the multipliers
+            // are recomputed from stationarity; a column whose recomputed multiplier is negative is
+            // dropped and the step repeated (same rule as gi_core.cuh).
+            if (n_drop == drops_at_refresh) break;
+            for (int pass = 0;; ++pass) {
+                const int q = S.isc[0];
+                symv_packed<D, NT>(S.Hp, S.x, S.wv);
+                __syncthreads();
+                for (int i = tid; i < nV; i += NT) S.wv[i] += S.g[i];
+                __syncthreads();
+                matvec_T_parts<D, NT, MG>(Mop, S.wv, S.part);
+                __syncthreads();
+                for (int j = tid; j < nV; j += NT) S.y[j] = S.part[j] + S.part[nV + j] + S.part[2 * nV + j];
+                __syncthreads();
+                matvec_N_parts<D, NT, MG>(Mop, S.y, q, S.part);
+                __syncthreads();
+                for (int i = tid; i < nV; i += NT) S.x[i] -= S.part[i] + S.part[nV + i] + S.part[2 * nV + i];
+                double ymin = 0.0, ymaxn = 0.0;
+                int lmin = 0x7fffffff;
+                for (int j = tid; j < q; j += NT) {
+                    const double yj = S.y[j];
+                    S.lam[j] = fmax(yj, 0.0);   // lam = K1'(Hx+g) (pre-step grad; J2 part is H-orthogonal to K1)
+                    ymaxn = fmin(ymaxn, -fabs(yj));
+                    if (yj < ymin) { ymin = yj; lmin = j; }
+                }
+                double gmin, gmaxn;
+                int gl, dummy;
+                block_argmin<NT>(ymin, lmin, S.red_val, S.red_idx, gmin, gl);
+                __syncthreads();
+                block_argmin<NT>(ymaxn, tid, S.red_val, S.red_idx, gmaxn, dummy);
+                if (tid == 0) S.isc[7] += 1;
+                __syncthreads();
+                drops_at_refresh = n_drop;
+                if (!(gmin < -1e-10 * (1.0 - gmaxn)) || pass >= 8) break;
+                drop_column(gl);
+                drops_at_refresh = n_drop;
             }
-            for (int j = tid; j < q; j += NT) S.lam[j] = fmax(S.y[j], 0.0);   // lam = K1'(Hx+g) (pre-step grad; J2 part is H-orthogonal to K1)
-            double dmax; int dummy;
-            block_argmin<NT>(-dxm, tid, S.red_val, S.red_idx, dmax, dummy);
-            if (tid == 0) S.isc[7] += 1;
-            __syncthreads();
-            if (-dmax < 1e-13) break;
             continue;
         }
         const int pslot = pcode >> 1, pside = (pcode & 1) ? +1 : -1;
@@ -691,41 +741,7 @@ __global__ void __launch_bounds__(NT, 1) ltvmpc_fused_v1_kernel(BatchArgs a) {
                 __syncthreads();
             } else {
                 // P6b: drop active constraint l
-                const int l = S.isc[4];
-                for (int i = tid; i < nV; i += NT) S.kv[i] = ldM<MG>(&Mop[i * LD + l]);
-                __syncthreads();
-                symv_packed<D, NT>(S.Hp, S.kv, S.wv);
-                __syncthreads();
-                matvec_T_parts<D, NT, MG>(Mop, S.wv, S.part);     // all columns; only j<q, j!=l used
-                if (warp == 0) {
-                    double acc = 0.0;
-                    for (int i = lane; i < nV; i += 32) acc += S.kv[i] * S.wv[i];
-                    acc = warp_sum(acc);
-                    if (lane == 0) S.sc[4] = acc;
-                }
-                __syncthreads();
-                const double kHk = S.sc[4];
-                for (int j = tid; j < q; j += NT)
-                    S.z[j] = -(S.part[j] + S.part[nV + j] + S.part[2 * nV + j]) / kHk;   // r'
-                __syncthreads();
-                for (int tt = tid; tt < nV * q; tt += NT) {
-                    const int i = tt / q, j = tt - i * q;
-                    if (j != l) Mop[i * LD + j] = ldM<MG>(&Mop[i * LD + j]) + S.kv[i] * S.z[j];
-                }
-                __syncthreads();
-                const double rs = rsqrt(kHk);
-                for (int i = tid; i < nV; i += NT) {
-                    if (l != q - 1) Mop[i * LD + l] = ldM<MG>(&Mop[i * LD + q - 1]);
-                    Mop[i * LD + q - 1] = S.kv[i] * rs;
-                }
-                if (tid == 0) {
-                    S.status[S.act[l] >> 1] = 0;
-                    S.act[l] = S.act[q - 1];
-                    S.lam[l] = S.lam[q - 1];
-                    S.isc[0] = q - 1;
-                }
-                ++n_drop;
-                __syncthreads();
+                drop_column(S.isc[4]);
             }
         }
         if (S.isc[3] == STEP_INFEAS) break;

@@ -559,6 +559,9 @@ struct GiOps {
                     }
                     matvec_T(S, m, ybuf, S.nvec[cidx], extra, y, dsum);
                 }
+                // z = J2 y2 needs only y: issued here so that its FMAs and reduce-scatter shuffles interleave
+                // with the reductions of the step-length phase (independent dependency chains)
+                matvec_N(S, m, y, q, nV);
                 PHASE(5);
                 bool more = true;                   // (piggy-backed only) keep going with this candidate
                 if (KB > 1 && piggy) {
@@ -598,9 +601,8 @@ struct GiOps {
                     primal = !isinf(t2);
                     t = full ? t2 : t1;
                     PHASE(6);
-                    // P5: z = J2 y2, x += t z  (this warp's rows only)
+                    // P5: x += t z  (this warp's rows only)
                     if (primal) {
-                        matvec_N(S, m, y, q, nV);
                         if (lane < RPW) {
                             const int i = row0 + lane;
                             if (i < nV) S.x[i] += t * S.zrow[i];

@@ -78,3 +78,25 @@ def test_fused_step_matches_golden(mpc, fixture, tid):
     r = mpc.ltvmpc_dynamic_curvilinear(g["x0"], c_layout(g["x_ref"]), DT, c_layout(g["x_lin"]), c_layout(g["u_lin"]),
                                        track_id=np.full(B, tid, np.int32), param_id=np.full(B, pid, np.int32))
     _check(r, g)
+
+
+def test_hard_cases_match_oracle(mpc):
+    """The problems of the synthetic bench batches with the longest pivot sequences (hundreds of partial steps) and
+    the two on which earlier kernel variants stopped at a point with a negative recomputed multiplier
+    (|du| ~ 1e-2): scripts/make_hard_cases.py.  Kinematic and dynamic model, oracle solutions."""
+    import fsae_mpc_b200 as fm
+    g = load_golden("hard_cases.npz")
+    pid = _dyn_params(mpc)
+    for tag, model, tid in (("dyn", fm.DYNAMIC, 1), ("kin", fm.KINEMATIC, 0)):
+        B = g[tag + "_x0"].shape[0]
+        step = mpc.ltvmpc_dynamic_curvilinear if model == fm.DYNAMIC else mpc.ltvmpc_kinetmatic_curvilinear
+        kw = dict(track_id=np.full(B, tid, np.int32))
+        if model == fm.DYNAMIC:
+            kw["param_id"] = np.full(B, pid, np.int32)
+        r = step(g[tag + "_x0"], g[tag + "_x_ref"], DT, g[tag + "_x_lin"], g[tag + "_u_lin"], **kw)
+        assert np.array_equal(r.exitflag, g[tag + "_exitflag"].astype(np.int32)), tag
+        scale = np.maximum(1.0, np.max(np.abs(g[tag + "_u_opt"]), axis=1))
+        du = np.max(np.abs(r.u_opt - g[tag + "_u_opt"]), axis=1) / scale
+        assert du.max() <= U_RTOL, f"{tag}: max |du|inf rel = {du.max():.3e} at {du.argmax()}"
+        assert np.max(np.abs(r.fval - g[tag + "_fval"]) / (1 + np.abs(g[tag + "_fval"]))) <= 1e-9, tag
+        assert np.max(np.abs(r.slack_opt - g[tag + "_slack"])) <= 1e-7, tag
