@@ -452,10 +452,10 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
         const int kv = ctx->kernel_version;
         if (N == 40) rc = v1 ? launch_fused_v1<KinModel, 40, 256>(ctx, a, st)
                      : kv == 21 ? launch_fused_v2<KinModel, 40, 1, 8, 1>(ctx, a, st)     // 8 warps (1 CTA/SM: shared memory)
-                     : kv == 26 ? launch_fused_v2<KinModel, 40, 2, 6, 1>(ctx, a, st)     // 6 warps, one constraint per search
+                     : kv == 26 ? launch_fused_v2<KinModel, 40, 2, 6, 2>(ctx, a, st)     // 6 warps, blocks of 2 constraints per search
                      : kv == 28 ? launch_fused_v2<KinModel, 40, 2, 6, 3>(ctx, a, st)     // 6 warps, blocks of 3
                      : kv == 29 ? launch_fused_v2<KinModel, 40, 2, 4, 1>(ctx, a, st)     // 4 warps
-                     : launch_fused_v2<KinModel, 40, 2, 6, 2>(ctx, a, st);               // product: 6 warps, blocks of 2
+                     : launch_fused_v2<KinModel, 40, 2, 6, 1>(ctx, a, st);               // product: 6 warps, one constraint per search
         else if (N == 20) rc = v1 ? launch_fused_v1<KinModel, 20, 256>(ctx, a, st) : launch_fused_v2<KinModel, 20, 2>(ctx, a, st);
         else if (N == 80) rc = launch_fused_long<KinModel, 80>(ctx, a, st);
         else ctx->err = "kinematic fused step: horizon must be 20, 40 or 80";
