@@ -97,3 +97,4 @@ if __name__ == "__main__":
     perturbed("DYNAMIC", "fss2019", sel, tr, 8 if quick else 48, 2)
     sel, tr = lap("DYNAMIC", "fsg2019", 16, 2, n_sim=40 if quick else 1000)
     sel, tr = lap("KINEMATIC", "fso2020", 16, 2, n_sim=40 if quick else 1000)
+    sel, tr = lap("KINEMATIC", "fss2019", 16, 2, n_sim=40 if quick else 1000)
