@@ -407,10 +407,10 @@ static int launch_fused_long(fsae_ctx* ctx, BatchArgs a, cudaStream_t st) {
     return FSAE_OK;
 }
 
-template <class Model, int N, int MINB, int NW = 8, int KB = 1>
+template <class Model, int N, int MINB, int NW = 8, int KB = 1, int CSR = -1>
 static int launch_fused_v2(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
-    using S_t = SmemV2<Model, N, NW, KB>;
-    auto kern = ltvmpc_fused_v2_kernel<Model, N, MINB, NW, KB>;
+    using S_t = SmemV2<Model, N, NW, KB, CSR>;
+    auto kern = ltvmpc_fused_v2_kernel<Model, N, MINB, NW, KB, CSR>;
     static bool configured[64] = {false};
     if (!configured[ctx->device & 63]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S_t)));
@@ -419,6 +419,39 @@ static int launch_fused_v2(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
     kern<<<a.B, 32 * NW, sizeof(S_t), st>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
+    return FSAE_OK;
+}
+
+// Long horizons with the register-tiled kernel: NW warps, CSR of the column slots of the operator tile in
+// registers and the rest in shared memory; B_bar rows the constraints do not touch, the packed H and the
+// J staging in a per-problem global slab (L2-resident: <= 148 CTAs x 260 KB in flight).  Launched in
+// slices so the slab pool is bounded.
+template <class Model, int N, int NW, int CSR>
+static int launch_fused_v2_long(fsae_ctx* ctx, BatchArgs a, cudaStream_t st) {
+    using S_t = SmemV2<Model, N, NW, 1, CSR>;
+    constexpr int SLICE = 2048;
+    DevBuf& pool = ctx->m_scratch[st == ctx->stream2 ? 1 : 0];
+    const int nsl = a.B < SLICE ? a.B : SLICE;
+    CK(pool.reserve((size_t)nsl * S_t::SLAB * sizeof(double)));
+    const int B = a.B;
+    constexpr int NX = Model::NX, NU = Model::NU, NS = Model::NS, nU = NU * N, nV = nU + NS;
+    const int nC = Cons<Model>::n_ref_rows(N);
+    for (int lo = 0; lo < B; lo += SLICE) {
+        BatchArgs c = a;
+        c.B = (lo + SLICE <= B) ? SLICE : B - lo;
+        c.m_scratch = (double*)pool.p;
+        if (a.track_id) c.track_id = a.track_id + lo;
+        if (a.param_id) c.param_id = a.param_id + lo;
+        c.x0 = a.x0 + (size_t)lo * NX; c.x_ref = a.x_ref + (size_t)lo * NX * N;
+        c.x_lin = a.x_lin + (size_t)lo * NX * N; c.u_lin = a.u_lin + (size_t)lo * NU * N;
+        c.u_opt = a.u_opt + (size_t)lo * nU; c.x_opt = a.x_opt + (size_t)lo * NX * N;
+        c.exitflag = a.exitflag + lo; c.fval = a.fval + lo; c.slack_opt = a.slack_opt + (size_t)lo * NS;
+        if (a.iters) c.iters = a.iters + lo;
+        if (a.wsB) c.wsB = a.wsB + (size_t)lo * nV;
+        if (a.wsC) c.wsC = a.wsC + (size_t)lo * nC;
+        const int rc = launch_fused_v2<Model, N, 1, NW, 1, CSR>(ctx, c, st);
+        if (rc != FSAE_OK) return rc;
+    }
     return FSAE_OK;
 }
 
@@ -457,7 +490,8 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
                      : kv == 29 ? launch_fused_v2<KinModel, 40, 2, 4, 1>(ctx, a, st)     // 4 warps
                      : launch_fused_v2<KinModel, 40, 2, 6, 1>(ctx, a, st);               // product: 6 warps, one constraint per search
         else if (N == 20) rc = v1 ? launch_fused_v1<KinModel, 20, 256>(ctx, a, st) : launch_fused_v2<KinModel, 20, 2>(ctx, a, st);
-        else if (N == 80) rc = launch_fused_long<KinModel, 80>(ctx, a, st);
+        else if (N == 80) rc = v1 ? launch_fused_long<KinModel, 80>(ctx, a, st)          // operator in an L2 slab (cross-check)
+                          : launch_fused_v2_long<KinModel, 80, 12, 4>(ctx, a, st);  // 12 warps, 4 of 6 column slots in registers
         else ctx->err = "kinematic fused step: horizon must be 20, 40 or 80";
     } else {
         if (N == 40) rc = launch_fused_v2<DynModel, 40, 1>(ctx, a, st);

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256, 1) dense_qp_kernel(DenseArgs a) {
         Q.status[i] = (int8_t)side;
     }
     // H tiles (internal order) and the packed copy
-    double m[RPW][CS];
+    GiTile<G> m;
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int i = row0 + r;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256, 1) dense_qp_kernel(DenseArgs a) {
             const int j = lane + 32 * s;
             double v = 0.0;
             if (i < nCv && j < nCv) v = H[(size_t)S.perm[j] * nV + S.perm[i]];
-            m[r][s] = v;
+            m(r, s) = v;
             if (i < nV && j <= i) Q.Hp[G::hp(i, j)] = (i < nCv) ? v : (i == j ? a.flat_eps : 0.0);
         }
     }

@@ -22,22 +22,38 @@
 
 namespace fsae {
 
-template <class Model, int N, int NW_ = 8, int KB_ = 1>
-using CfgV2 = GiCfg<Dims<Model, N>::nV, NW_, KB_>;
+template <class Model, int N, int NW_ = 8, int KB_ = 1, int CSR_ = -1>
+using CfgV2 = GiCfg<Dims<Model, N>::nV, NW_, KB_, CSR_>;
 
-template <class Model, int N, int NW_ = 8, int KB_ = 1>
+// LONG (CSR_ >= 0, long horizons): part of the operator tile lives in shared memory (Msm, which
+// reuses the space of arrays that are dead once the tiles are filled), only the B_bar rows the
+// constraints touch stay in shared memory, and the other B_bar rows, the packed H and the J
+// staging live in a per-problem global slab that stays L2-resident.
+template <class Model, int N, int NW_ = 8, int KB_ = 1, int CSR_ = -1>
 struct SmemV2 {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
-    using G = CfgV2<Model, N, NW_, KB_>;
-    alignas(16) double Bf[C::NREAL * D::NPK];   // packed B_bar rows of the "real" states (kept to the end)
-    GiSm<G, D::NSLOT> gi;                       // x, g, packed H, working set, core scratch
-    double Ad[N * C::NREAL * D::NX];
+    using G = CfgV2<Model, N, NW_, KB_, CSR_>;
+    static constexpr bool LONG = G::CSS > 0;
+    static constexpr int NBF = LONG ? C::NCR : C::NREAL;                    // B_bar rows in shared memory
+    __host__ __device__ static constexpr int bfc(int c) { return LONG ? c : C::cons_real(c); }   // row of constraint state c
+    static constexpr size_t SLAB = LONG ? (size_t)C::NREAL * D::NPK + D::HP : 0;                  // doubles per problem
+    alignas(16) double Bf[NBF * D::NPK];        // packed B_bar rows (kept to the end)
+    GiSm<G, D::NSLOT, LONG> gi;                 // x, g, packed H, working set, core scratch
     double B1[D::NX * D::NU];
     double xf[N * D::NX];
-    alignas(16) double xl[N * D::NX];  // TMA bulk-copy destinations (16-byte aligned, sizes % 16 == 0)
-    alignas(16) double xr[N * D::NX];
-    alignas(16) double ul[N * D::NU];
+    union {
+        struct {                                // dead once the operator tiles are filled
+            double Ad[N * C::NREAL * D::NX];
+            alignas(16) double xl[N * D::NX];  // TMA bulk-copy destinations (16-byte aligned, sizes % 16 == 0)
+            alignas(16) double xr[N * D::NX];
+            alignas(16) double ul[N * D::NU];
+            double dd[N * D::NX];
+            double Kc[N * D::NU * D::NX];      // Riccati feedback gains K_s (adjoint rows -> J)
+            double wgram[6 * D::NX * D::NX + 3 * D::NU * D::NX];   // recursion scratch: W, P (double-buffered), W A, P A; B'P, S, K
+        };
+        alignas(16) double Msm[GiTile<G>::SM_DOUBLES > 0 ? GiTile<G>::SM_DOUBLES : 2];   // shared part of the operator tiles
+    };
     double pc[N * C::NPC];
     double g0[N * C::NG0];
     double cg[C::NCG];
@@ -47,12 +63,9 @@ struct SmemV2 {
     static constexpr int NGR = C::NCR * (C::NCR + 1) / 2;
     double gram[ROWNORMS ? N * NGR : 1];            // per step: Gram matrix of the constraint B_bar rows
     double csum[ROWNORMS ? N * C::NCR * D::NU : 1]; // per step: their sums over each control's columns
-    double dd[N * D::NX];
     double Gs[N * D::NU * D::NX];      // G_s = B' W_{s+1}: cost Gramian seen from the controls of step s
-    double Kc[N * D::NU * D::NX];      // Riccati feedback gains K_s (closed-loop chains -> J)
     double Wi[N * D::NU * D::NU];      // (Lambda_s)^(-T/2) / sqrt(2): the diagonal blocks of J
     double Lam3[N * 3];                // Lambda_s (a, b, d)
-    double wgram[6 * D::NX * D::NX + 3 * D::NU * D::NX];   // recursion scratch: W, P (double-buffered), W A, P A; B'P, S, K
     double scal[8];                    // 0 cost const
     alignas(8) fsae_params prm;        // this problem's parameter set (copied once: no global loads in the loops)
     alignas(8) unsigned long long mbar; // mbarrier of the input staging
@@ -83,12 +96,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
 // Problem policy of the core for the LTV-MPC QPs: slots [0, nV) are the variable bounds
 // (ltvmpc_*_curvilinear.m:28-29), slots nV + r*N + k the constraint row r at horizon step k
 // (cons.cuh).  Nothing dense is ever formed.
-template <class Model, int N, int NW_, int KB_>
+template <class Model, int N, int NW_, int KB_, int CSR_>
 struct MpcProb {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
-    using G = CfgV2<Model, N, NW_, KB_>;
-    SmemV2<Model, N, NW_, KB_>& S;
+    using G = CfgV2<Model, N, NW_, KB_, CSR_>;
+    using S_t = SmemV2<Model, N, NW_, KB_, CSR_>;
+    S_t& S;
     const fsae_params& P;
     double dt;
 
@@ -115,7 +129,7 @@ struct MpcProb {
                     const double2 xx = *reinterpret_cast<const double2*>(&x[j]);
 #pragma unroll
                     for (int c = 0; c < C::NCR; ++c) {
-                        const double2 bb = *reinterpret_cast<const double2*>(&S.Bf[C::cons_real(c) * D::NPK + D::pk(k, j)]);
+                        const double2 bb = *reinterpret_cast<const double2*>(&S.Bf[S_t::bfc(c) * D::NPK + D::pk(k, j)]);
                         acc[c] = fma(bb.x, xx.x, fma(bb.y, xx.y, acc[c]));
                     }
 #pragma unroll
@@ -204,7 +218,7 @@ struct MpcProb {
         acc += (step == p.k) ? ((uc == 0) ? p.cu[0] : p.cu[NU - 1]) : 0.0;
         const int idx = in ? D::pk(p.k, i) : 0;
 #pragma unroll
-        for (int c = 0; c < C::NCR; ++c) acc = fma(p.creal[c], S.Bf[C::cons_real(c) * D::NPK + idx], acc);
+        for (int c = 0; c < C::NCR; ++c) acc = fma(p.creal[c], S.Bf[S_t::bfc(c) * D::NPK + idx], acc);
         return in ? acc : ((i == p.slack) ? 1.0 : 0.0);
     }
 
@@ -214,12 +228,13 @@ struct MpcProb {
     __device__ __forceinline__ bool is_unit(int pslot) const { return pslot < D::nV; }
 };
 
-template <class Model, int N, int MINB, int NW_ = 8, int KB_ = 1>
+template <class Model, int N, int MINB, int NW_ = 8, int KB_ = 1, int CSR_ = -1>
 __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchArgs a) {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
-    using G = CfgV2<Model, N, NW_, KB_>;
-    using S_t = SmemV2<Model, N, NW_, KB_>;
+    using G = CfgV2<Model, N, NW_, KB_, CSR_>;
+    using S_t = SmemV2<Model, N, NW_, KB_, CSR_>;
+    constexpr bool LONG = S_t::LONG;
     constexpr int NX = D::NX, NU = D::NU, NS = D::NS, nU = D::nU, nV = D::nV;
     constexpr int NT = G::NT, NW = G::NW, RPW = G::RPW, CS = G::CS, RP = G::RP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -235,6 +250,9 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     const DevTrack tr = a.tracks[a.track_id ? a.track_id[b] : 0];
     const double dt = a.dt;
     const int row0 = warp * RPW;            // first row of this warp
+    // all real-state rows of B_bar: shared memory, or (LONG) the problem's global slab [B_bar rows | packed H]
+    double* const bf_all = LONG ? a.m_scratch + (size_t)b * S_t::SLAB : S.Bf;
+    if (LONG && tid == 0) S.gi.hpg = a.m_scratch + (size_t)b * S_t::SLAB + (size_t)C::NREAL * D::NPK;
 
     STAGE_DECL;
     // ---------------------------------------------------------------- load (TMA bulk copies)
@@ -489,7 +507,11 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
                     for (int r = 0; r < NX; ++r) v[r] = vn[r];
                 }
 #pragma unroll
-                for (int ii = 0; ii < C::NREAL; ++ii) S.Bf[ii * D::NPK + D::pk(k, t)] = v[C::real_state(ii)];
+                for (int ii = 0; ii < C::NREAL; ++ii) bf_all[ii * D::NPK + D::pk(k, t)] = v[C::real_state(ii)];
+                if (LONG) {
+#pragma unroll
+                    for (int c = 0; c < C::NCR; ++c) S.Bf[c * D::NPK + D::pk(k, t)] = v[C::real_state(C::cons_real(c))];
+                }
             }
         }
     }
@@ -514,7 +536,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
                     for (int u = 0; u < NU; ++u) {
                         double bc[C::NCR];
 #pragma unroll
-                        for (int c = 0; c < C::NCR; ++c) bc[c] = S.Bf[C::cons_real(c) * D::NPK + D::pk(k, j + u)];
+                        for (int c = 0; c < C::NCR; ++c) bc[c] = S.Bf[S_t::bfc(c) * D::NPK + D::pk(k, j + u)];
                         int gi = 0;
 #pragma unroll
                         for (int c = 0; c < C::NCR; ++c) {
@@ -540,7 +562,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
                     for (int ii = 0; ii < C::NREAL; ++ii) {
                         const int r = C::real_state(ii);
                         const double q = (k == N - 1) ? P.Q_terminal[r] : P.Q[r];
-                        acc += q * S.Bf[ii * D::NPK + D::pk(k, j)] * e[k * NX + r];
+                        acc += q * bf_all[ii * D::NPK + D::pk(k, j)] * e[k * NX + r];
                     }
 #pragma unroll
                     for (int ii = 0; ii < C::NINT; ++ii) {
@@ -599,7 +621,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
 #pragma unroll
                     for (int c = 0; c < C::NCR; ++c) {
                         aS += ac[c] * S.csum[(k * C::NCR + c) * NU + u];
-                        aB += ac[c] * S.Bf[C::cons_real(c) * D::NPK + D::pk(k, NU * k + u)];
+                        aB += ac[c] * S.Bf[S_t::bfc(c) * D::NPK + D::pk(k, NU * k + u)];
                     }
                     const double cu = C::row_ucoef(r, u, pc, S.cg);
                     n2 += bu[u] * (2.0 * aS + (double)(k + 1) * bu[u]) + cu * (2.0 * (aB + bu[u]) + cu);
@@ -617,7 +639,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
         {
             static_assert(NU * D::NPK <= D::HP, "J staging must fit the packed-H region");
             static_assert(WNT >= nU, "one worker thread per row of J");
-            double* Jst = S.gi.Hp;
+            double* Jst = S.gi.hp();
             const int t = wtid - (WNT - nU);
             const int wfirst = (WNT - nU) >> 5;                 // first worker warp that owns rows
             if ((wtid >> 5) >= wfirst) {
@@ -671,13 +693,14 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     // ---------------------------------------------------------------- operator tiles, packed H
     // M = [ e_{nU}, .., e_{nU+NS-1} | J ]: the NS flat (zero-curvature) slack variables start with their
     // lower bound in the working set (q = NS, lam = R_soft: dual feasible), J (J'HJ = I) from the staging.
-    using Ops = GiOps<G, GiSm<G, D::NSLOT>>;
-    GiSm<G, D::NSLOT>& Q = S.gi;
-    double m[RPW][CS];
+    using Ops = GiOps<G, GiSm<G, D::NSLOT, LONG>>;
+    GiSm<G, D::NSLOT, LONG>& Q = S.gi;
+    GiTile<G> m;
     double lam[CS];
     int q = NS, ybuf = 0;
     {
-        const double* Jst = S.gi.Hp;
+        const double* Jst = S.gi.hp();
+        if (LONG) m.attach(S.Msm);
 #pragma unroll
         for (int s = 0; s < CS; ++s) {
             const int jj = lane + 32 * s, j = jj - NS;
@@ -697,7 +720,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
                         for (int r2 = 0; r2 < NU; ++r2) v = fma(jr[r2], S.Wi[sj * NU * NU + r2 * NU + cj], v);
                     }
                 }
-                m[r][s] = v;
+                m(r, s) = v;
             }
             lam[s] = (jj < NS) ? fabs(S.gi.g[nU + jj]) : 0.0;
         }
@@ -720,7 +743,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
                 const double* Gr = S.Gs + (si * NU + ci) * NX;
                 double acc = 0.0;
 #pragma unroll
-                for (int ii = 0; ii < C::NREAL; ++ii) acc = fma(Gr[ii], S.Bf[ii * D::NPK + D::pk(si, j)], acc);
+                for (int ii = 0; ii < C::NREAL; ++ii) acc = fma(Gr[ii], bf_all[ii * D::NPK + D::pk(si, j)], acc);
 #pragma unroll
                 for (int ii = 0; ii < C::NINT; ++ii)
                     if (C::int_ucol(ii) == cj) acc = fma(Gr[C::int_state(ii)], dt, acc);
@@ -728,7 +751,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
                 if (i == j) h += 2.0 * P.R[ci];
             }
             if (gH) { gH[(size_t)j * nV + i] = h; gH[(size_t)i * nV + j] = h; }
-            S.gi.Hp[D::hp(i, j)] = (i >= nU) ? (i == j ? P.flat_eps : 0.0) : h;
+            S.gi.hp()[D::hp(i, j)] = (i >= nU) ? (i == j ? P.flat_eps : 0.0) : h;
         }
     }
     if (a.dbg_g) {
@@ -744,7 +767,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     STAGE(5);
     Ops::initial_point(Q, m, ybuf, q, nU, nV);             // x_u = -J J' g, slacks at 0
     STAGE(6);
-    const MpcProb<Model, N, NW_, KB_> prob{S, P, dt};
+    const MpcProb<Model, N, NW_, KB_, CSR_> prob{S, P, dt};
     const GiStats st = Ops::solve(prob, Q, m, lam, q, ybuf, nV, P.feas_tol, P.max_iter > 0 ? P.max_iter : 5 * (nV + C::n_ref_rows(N)));
     const int iters = st.iters, exitflag = st.exitflag, n_add = st.n_add, n_drop = st.n_drop, n_refresh = st.n_refresh;
 
@@ -777,7 +800,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             int c = 0, k = 0;
             if (rid < NRR) {
                 c = rid / N; k = rid - c * N;
-                const double* row = S.Bf + c * D::NPK + D::pk(k, 0);
+                const double* row = bf_all + c * D::NPK + D::pk(k, 0);
                 const int len = NU * (k + 1);
                 const int ch = (len + 3) >> 2;
                 const int j0 = part * ch, j1 = (j0 + ch < len) ? j0 + ch : len;

@@ -96,7 +96,7 @@ __device__ __forceinline__ double warp_reduce_scatter(double (&v)[RH]) {
 }
 
 // Tile geometry for at most NVMAX variables and NW warps per CTA.
-template <int NVMAX, int NW_ = 8, int KB_ = 1>
+template <int NVMAX, int NW_ = 8, int KB_ = 1, int CSR_ = -1>
 struct GiCfg {
     static constexpr int NW = NW_, NT = 32 * NW_;
     static constexpr int KB = KB_;                           // constraints projected per search (block size)
@@ -106,6 +106,8 @@ struct GiCfg {
     static constexpr int RP = RPW * NW;                      // padded rows
     static constexpr int CS = (NVMAX + 32) / 32;             // column slots per lane (one spare column)
     static constexpr int CP = CS * 32;                       // padded columns
+    static constexpr int CSR = (CSR_ < 0 || CSR_ > CS) ? CS : CSR_;   // column slots held in registers ...
+    static constexpr int CSS = CS - CSR;                     // ... and in shared memory (long horizons)
     static constexpr int RH = (RPW <= 8) ? 8 : (RPW <= 16 ? 16 : 32);   // reduce-scatter width
     static constexpr int HP = NVMAX * (NVMAX + 1) / 2;       // packed lower triangle
     static_assert(RPW <= 32, "reduce-scatter network supports up to 32 rows per warp");
@@ -113,12 +115,37 @@ struct GiCfg {
     __host__ __device__ static constexpr int hp(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 };
 
+// Operator tile of one thread: RPW rows x CS column slots.  The first CSR slots live in registers, the
+// remaining CSS = CS - CSR in shared memory (long horizons: the operator of nV = 161 does not fit the
+// register file of one SM).  Slot indices are compile-time constants after unrolling, so the choice
+// folds away; the shared part is laid out [warp][row][slot][lane] (conflict-free).
+template <class G>
+struct GiTile {
+    static constexpr int RPW = G::RPW, CSR = G::CSR, CSS = G::CSS;
+    double reg[RPW][CSR];
+    double* sm;            // this thread's first shared-memory element
+    static constexpr int SM_DOUBLES = G::NW * RPW * (CSS > 0 ? CSS : 0) * 32;
+    __device__ __forceinline__ void attach(double* base) {
+        sm = base + (size_t)(threadIdx.x >> 5) * RPW * CSS * 32 + (threadIdx.x & 31);
+    }
+    __device__ __forceinline__ double& operator()(int r, int s) {
+        if (CSS == 0 || s < CSR) return reg[r][s < CSR ? s : 0];
+        return sm[(r * CSS + (s - CSR)) * 32];
+    }
+    __device__ __forceinline__ const double& operator()(int r, int s) const {
+        if (CSS == 0 || s < CSR) return reg[r][s < CSR ? s : 0];
+        return sm[(r * CSS + (s - CSR)) * 32];
+    }
+};
+
 // Shared-memory working set of the core.
-template <class G, int NSLOT>
+template <class G, int NSLOT, bool HPG = false>
 struct GiSm {
     alignas(16) double x[G::RP];
     double g[G::RP];
-    double Hp[G::HP];                  // packed lower triangle of H (drops, refresh, fval)
+    double Hp[HPG ? 2 : G::HP];        // packed lower triangle of H (drops, refresh, fval) ...
+    double* hpg;                       // ... or, for long horizons, a per-problem global (L2-resident) slab
+    __device__ __forceinline__ double* hp() { return HPG ? hpg : Hp; }
     double ypart[G::YB][G::NW][G::CP]; // cross-warp partial sums of M'v (double-buffered; one buffer per block member)
     double colk[2][G::RP];             // column broadcast (factorisation / column q / drop column)
     double rowv[G::RP];                // per-warp row vector scratch (gradient / H k)
@@ -146,7 +173,7 @@ struct GiOps {
 
     // y = M' v for a row vector v (shared, per-warp rows); y for this lane's columns, identical
     // in every warp.  The spare padded column CP-1 carries sum over warps of `extra`.
-    __device__ __forceinline__ static void matvec_T(SM& S, const double (&m)[RPW][CS], int& ybuf,
+    __device__ __forceinline__ static void matvec_T(SM& S, const GiTile<G>& m, int& ybuf,
                                                     const double* rowvec, double extra,
                                                     double (&y)[CS], double& extra_sum) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row0 = warp * RPW;
@@ -157,7 +184,7 @@ struct GiOps {
         for (int r = 0; r < RPW; ++r) {
             const double v = rowvec[row0 + r];
 #pragma unroll
-            for (int s = 0; s < CS; ++s) yp[s] += m[r][s] * v;
+            for (int s = 0; s < CS; ++s) yp[s] += m(r, s) * v;
         }
         if (lane == 31) yp[CS - 1] = extra;
 #pragma unroll
@@ -176,7 +203,7 @@ struct GiOps {
     }
 
     // z = sum_{q0 <= j < nV} M[:, j] y_j for this warp's rows -> S.zrow, visible after __syncwarp
-    __device__ __forceinline__ static void matvec_N(SM& S, const double (&m)[RPW][CS], const double (&y)[CS],
+    __device__ __forceinline__ static void matvec_N(SM& S, const GiTile<G>& m, const double (&y)[CS],
                                                     int q0, int nV) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row0 = warp * RPW;
         double zp[RH];
@@ -187,7 +214,7 @@ struct GiOps {
             const int j = lane + 32 * s;
             const double yj = (j >= q0 && j < nV) ? y[s] : 0.0;
 #pragma unroll
-            for (int r = 0; r < RPW; ++r) zp[r] += m[r][s] * yj;
+            for (int r = 0; r < RPW; ++r) zp[r] += m(r, s) * yj;
         }
         const double zr = warp_reduce_scatter<RH>(zp);
         constexpr int SH = (RH == 32) ? 0 : (RH == 16 ? 1 : 2);
@@ -205,7 +232,7 @@ struct GiOps {
             const int pt = t / nV, i = t - pt * nV;
             const int j0 = pt * CH, j1 = (j0 + CH < nV) ? j0 + CH : nV;
             double acc = 0.0;
-            for (int j = j0; j < j1; ++j) acc += ((j <= i) ? S.Hp[G::hp(i, j)] : S.Hp[G::hp(j, i)]) * v[j];
+            for (int j = j0; j < j1; ++j) acc += ((j <= i) ? S.hp()[G::hp(i, j)] : S.hp()[G::hp(j, i)]) * v[j];
             S.wpart[pt][i] = acc;
         }
         __syncthreads();
@@ -222,7 +249,7 @@ struct GiOps {
     // The ns flat (zero-curvature) variables start with one bound in the working set:
     // q = ns, lam_j = |g_flat_j|.  One column broadcast + one barrier per elimination step.
     // Returns false (uniformly) if a pivot is not positive.
-    __device__ static bool factor_and_layout(SM& S, double (&m)[RPW][CS], double (&lam)[CS], int& q,
+    __device__ static bool factor_and_layout(SM& S, GiTile<G>& m, double (&lam)[CS], int& q,
                                              int nC, int ns, int nV) {
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row0 = warp * RPW;
         bool ok = true;
@@ -233,7 +260,7 @@ struct GiOps {
                 for (int s = 0; s < CS; ++s)
                     if (s == ks) {
 #pragma unroll
-                        for (int r = 0; r < RPW; ++r) S.colk[buf][row0 + r] = m[r][s];
+                        for (int r = 0; r < RPW; ++r) S.colk[buf][row0 + r] = m(r, s);
                     }
             }
             __syncthreads();
@@ -256,7 +283,7 @@ struct GiOps {
                     for (int r = 0; r < RPW; ++r) {
                         const double vr = S.colk[buf][row0 + r];
 #pragma unroll
-                        for (int s = sb; s < CS; ++s) m[r][s] = fma(-vr, lj[s], m[r][s]);
+                        for (int s = sb; s < CS; ++s) m(r, s) = fma(-vr, lj[s], m(r, s));
                     }
                 }
             }
@@ -268,7 +295,7 @@ struct GiOps {
 #pragma unroll
                         for (int s = 0; s < CS; ++s) {
                             const int j = lane + 32 * s;
-                            if (j > k && j < nC) m[r][s] = -lj[s];
+                            if (j > k && j < nC) m(r, s) = -lj[s];
                         }
                     }
             }
@@ -283,8 +310,8 @@ struct GiOps {
             for (int r = 0; r < RPW; ++r) {
                 const int i = row0 + r;
                 double v = 0.0;
-                if (j < nC && i < nC) v = (i < j) ? m[r][s] * sc : (i == j ? sc : 0.0);
-                m[r][s] = v;
+                if (j < nC && i < nC) v = (i < j) ? m(r, s) * sc : (i == j ? sc : 0.0);
+                m(r, s) = v;
             }
         }
         // rotate the J columns right by ns lanes (K1 first): column j comes from column j - ns
@@ -294,8 +321,8 @@ struct GiOps {
             for (int s = 0; s < CS; ++s) {
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) {
-                    const double same = __shfl_sync(0xffffffffu, m[r][s], (lane - ns) & 31);
-                    const double prev = (s > 0) ? __shfl_sync(0xffffffffu, m[r][s - 1], (lane - ns) & 31) : 0.0;
+                    const double same = __shfl_sync(0xffffffffu, m(r, s), (lane - ns) & 31);
+                    const double prev = (s > 0) ? __shfl_sync(0xffffffffu, m(r, s > 0 ? s - 1 : 0), (lane - ns) & 31) : 0.0;
                     t[r][s] = (lane >= ns) ? same : prev;
                 }
             }
@@ -305,7 +332,7 @@ struct GiOps {
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) {
                     const int i = row0 + r;
-                    m[r][s] = (j < ns) ? ((i == nC + j) ? 1.0 : 0.0) : (j < nV ? t[r][s] : 0.0);
+                    m(r, s) = (j < ns) ? ((i == nC + j) ? 1.0 : 0.0) : (j < nV ? t[r][s] : 0.0);
                 }
             }
         }
@@ -319,7 +346,7 @@ struct GiOps {
     }
 
     // x_c = -J2 J2' g for the curved variables (flat ones keep the bound the caller put in x)
-    __device__ static void initial_point(SM& S, const double (&m)[RPW][CS], int& ybuf, int q, int nC, int nV) {
+    __device__ static void initial_point(SM& S, const GiTile<G>& m, int& ybuf, int q, int nC, int nV) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row0 = warp * RPW;
         double y[CS], dummy;
         matvec_T(S, m, ybuf, S.g, 0.0, y, dummy);
@@ -344,7 +371,7 @@ struct GiOps {
     // the adds of a block x, z and the tile updates are warp-local: the only block barrier of a
     // piggy-backed add is the one inside the projection.
     template <class Prob>
-    __device__ static GiStats solve(const Prob& prob, SM& S, double (&m)[RPW][CS], double (&lam)[CS], int& q,
+    __device__ static GiStats solve(const Prob& prob, SM& S, GiTile<G>& m, double (&lam)[CS], int& q,
                                     int& ybuf, int nV, double tol, int max_iter) {
         constexpr int KB = G::KB;
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row0 = warp * RPW;
@@ -360,7 +387,7 @@ struct GiOps {
                 for (int s = 0; s < CS; ++s)
                     if (s == ls) {
 #pragma unroll
-                        for (int r = 0; r < RPW; ++r) S.colk[1][row0 + r] = m[r][s];
+                        for (int r = 0; r < RPW; ++r) S.colk[1][row0 + r] = m(r, s);
                     }
             }
             __syncthreads();                                 // k = M[:, l] visible block-wide
@@ -379,22 +406,22 @@ struct GiOps {
 #pragma unroll
                 for (int s = 0; s < CS; ++s) {
                     const int j = lane + 32 * s;
-                    if (j < q && j != l) m[r][s] -= kr * (rp[s] * ik);
+                    if (j < q && j != l) m(r, s) -= kr * (rp[s] * ik);
                 }
                 double last = 0.0;
 #pragma unroll
                 for (int s = 0; s < CS; ++s)
-                    if (s == q1s) last = m[r][s];
+                    if (s == q1s) last = m(r, s);
                 last = __shfl_sync(0xffffffffu, last, q1l);
 #pragma unroll
                 for (int s = 0; s < CS; ++s) {
                     const int j = lane + 32 * s;
-                    if (j == l && l != q1) m[r][s] = last;
+                    if (j == l && l != q1) m(r, s) = last;
                 }
 #pragma unroll
                 for (int s = 0; s < CS; ++s) {
                     const int j = lane + 32 * s;
-                    if (j == q1) m[r][s] = kr * rs;
+                    if (j == q1) m(r, s) = kr * rs;
                 }
             }
             double lam_last = 0.0;
@@ -538,7 +565,7 @@ struct GiOps {
                         for (int r = 0; r < RPW; ++r)
                             if (r == pr) {
 #pragma unroll
-                                for (int s = 0; s < CS; ++s) S.ypart[ybuf][0][lane + 32 * s] = m[r][s];
+                                for (int s = 0; s < CS; ++s) S.ypart[ybuf][0][lane + 32 * s] = m(r, s);
                             }
                         if (KB > 1 && piggy && lane == 31) S.ypart[ybuf][0][G::CP - 1] = S.x[pslot] - S.xs0[pslot];
                     }
@@ -633,7 +660,7 @@ struct GiOps {
                             for (int s = 0; s < CS; ++s)
                                 if (s == qs) {
 #pragma unroll
-                                    for (int r = 0; r < RPW; ++r) S.colk[0][row0 + r] = m[r][s];
+                                    for (int r = 0; r < RPW; ++r) S.colk[0][row0 + r] = m(r, s);
                                 }
                         }
                         __syncwarp();
@@ -669,9 +696,9 @@ struct GiOps {
                                     const double wr = (zr + sgd * S.colk[0][row0 + r]) * beta;
 #pragma unroll
                                     for (int s = 0; s < CS; ++s) {
-                                        if (s < qq) m[r][s] = fma(-kr, y[s], m[r][s]);
-                                        else if (s > qq) m[r][s] = fma(-wr, y[s], m[r][s]);
-                                        else m[r][s] = fma(-wr, ybq, fma(-kr, yaq, ccq * m[r][s]));
+                                        if (s < qq) m(r, s) = fma(-kr, y[s], m(r, s));
+                                        else if (s > qq) m(r, s) = fma(-wr, y[s], m(r, s));
+                                        else m(r, s) = fma(-wr, ybq, fma(-kr, yaq, ccq * m(r, s)));
                                     }
                                 }
                             }
