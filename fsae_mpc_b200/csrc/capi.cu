@@ -489,7 +489,10 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
                      : kv == 28 ? launch_fused_v2<KinModel, 40, 2, 6, 3>(ctx, a, st)     // 6 warps, blocks of 3
                      : kv == 29 ? launch_fused_v2<KinModel, 40, 2, 4, 1>(ctx, a, st)     // 4 warps
                      : launch_fused_v2<KinModel, 40, 2, 6, 1>(ctx, a, st);               // product: 6 warps, one constraint per search
-        else if (N == 20) rc = v1 ? launch_fused_v1<KinModel, 20, 256>(ctx, a, st) : launch_fused_v2<KinModel, 20, 2>(ctx, a, st);
+        else if (N == 20) rc = v1 ? launch_fused_v1<KinModel, 20, 256>(ctx, a, st)
+                          : kv == 21 ? launch_fused_v2<KinModel, 20, 2, 8, 1>(ctx, a, st)      // 8 warps x 2 CTAs/SM: 3.36M QP/s
+                          : kv == 26 ? launch_fused_v2<KinModel, 20, 3, 6, 1>(ctx, a, st)      // 6 warps x 3: 4.39M
+                          : launch_fused_v2<KinModel, 20, 5, 4, 1>(ctx, a, st);                // 4 warps x 5 CTAs/SM: 4.63M (13 KB operator)
         else if (N == 80) rc = v1 ? launch_fused_long<KinModel, 80>(ctx, a, st)          // operator in an L2 slab (cross-check)
                           : launch_fused_v2_long<KinModel, 80, 12, 4>(ctx, a, st);  // 12 warps, 4 of 6 column slots in registers
         else ctx->err = "kinematic fused step: horizon must be 20, 40 or 80";

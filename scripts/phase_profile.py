@@ -24,6 +24,11 @@ lib.fsae_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
 lib.fsae_profile_read_stages.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
 sg = (C.c_uint64 * 16)()
 x0, xr, xl, ul = wl.perturbed_batch("kinematic", "fsg2019", B, 0)
+if os.environ.get("FSAE_N") == "80":          # horizon 80: the committed fsg2019 lap, unperturbed
+    g = dict(np.load(os.path.join(wl.GOLDEN, "kinematic_lap_fsg2019_N80.npz")))
+    pick = np.arange(B) % g["x0"].shape[0]
+    tr_ = lambda a: np.ascontiguousarray(a.transpose(0, 2, 1)[pick])
+    x0, xr, xl, ul = g["x0"][pick].copy(), tr_(g["x_ref"]), tr_(g["x_lin"]), tr_(g["u_lin"])
 out = (C.c_uint64 * 16)()
 mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, 0.05, xl, ul)
 lib.fsae_profile_read(mpc._ctx, out, 1)
