@@ -294,6 +294,12 @@ class FsaeMpc:
     def stream(self):
         return int(self._lib.fsae_stream(self._ctx) or 0)
 
+    def set_taps(self, d_H=0, d_g=0, d_M=0):
+        """Device addresses (0 = off) that the next ltvmpc_dev calls fill with H, g and the initial
+        operator M = [e_slack | J] of every problem (fsae_debug_set_taps; tests)."""
+        self._check(self._lib.fsae_debug_set_taps(self._ctx, C.c_void_p(d_H or None), C.c_void_p(d_g or None),
+                                                  C.c_void_p(d_M or None)), "fsae_debug_set_taps")
+
     def set_kernel_version(self, v):
         """2 = register-tiled product kernel (default), 1 = shared-memory cross-check variant."""
         return int(self._lib.fsae_debug_set_kernel_version(self._ctx, int(v)))

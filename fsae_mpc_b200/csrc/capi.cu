@@ -45,6 +45,7 @@ struct fsae_ctx {
     std::string err;
     int64_t launches = 0;
     int kernel_version = 2;     // 1 = shared-memory operator (cross-check), 2 = register-tiled
+    double *tap_H = nullptr, *tap_g = nullptr, *tap_M = nullptr;   // device buffers of the debug taps (tests)
     fsae_params h_params[FSAE_MAX_PARAM_SETS];
     fsae_params* d_params = nullptr;
     DevTrack h_tracks[FSAE_MAX_TRACKS];
@@ -477,6 +478,7 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
     a.iters = iters; a.wsB = workingSetB; a.wsC = workingSetC;
     a.tracks = ctx->d_tracks; a.params = ctx->d_params;
     a.counters = ctx->d_counters;
+    a.dbg_H = ctx->tap_H; a.dbg_g = ctx->tap_g; a.dbg_M = ctx->tap_M;
     CK(cudaEventRecord(ctx->ev0, st));
     int rc = FSAE_ERR_UNSUPPORTED;
     if (model == FSAE_MODEL_KINEMATIC) {
@@ -806,6 +808,15 @@ extern "C" int fsae_probe_fp64_tflops(fsae_ctx* ctx, double* tflops) {
     }
     ctx->ev_valid = false;
     *tflops = best;
+    return FSAE_OK;
+}
+
+// Debug taps of the fused kernel (tests): device buffers that the NEXT fsae_ltvmpc_dev calls fill with the
+// condensed Hessian H [nV x nV x B], the gradient g [nV x B] and the initial dual active-set operator
+// M = [e_slack | J] [nV x nV x B] (column-major per problem).  Null pointers switch a tap off.
+extern "C" int fsae_debug_set_taps(fsae_ctx* ctx, double* d_H, double* d_g, double* d_M) {
+    if (!ctx) return FSAE_ERR_ARG;
+    ctx->tap_H = d_H; ctx->tap_g = d_g; ctx->tap_M = d_M;
     return FSAE_OK;
 }
 

@@ -38,6 +38,7 @@ struct BatchArgs {
     // optional debug taps (tests): H [nV x nV] column-major, g [nV], per problem
     double* dbg_H;
     double* dbg_g;
+    double* dbg_M;                  // initial operator M = [e_slack | J] [nV x nV] column-major (register-tiled kernel)
     unsigned long long* counters;   // [0] adds, [1] drops, [2] refreshes (atomicAdd per problem)
     double* m_scratch;              // per-CTA operator slabs for the long-horizon (global-operator) variant
 };

@@ -725,6 +725,18 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             lam[s] = (jj < NS) ? fabs(S.gi.g[nU + jj]) : 0.0;
         }
     }
+    if (a.dbg_M) {
+        double* gM = a.dbg_M + (size_t)b * nV * nV;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const int i = row0 + r;
+#pragma unroll
+            for (int s = 0; s < CS; ++s) {
+                const int j = lane + 32 * s;
+                if (i < nV && j < nV) gM[(size_t)j * nV + i] = m(r, s);
+            }
+        }
+    }
     __syncthreads();           // staging consumed: the region becomes the packed H
     // generate_qp.m:29  H = 2 (B' Qbar B + Rbar), packed lower triangle for the symv's (drops, refresh,
     // objective).  Entry (i, j), i >= j, i the later control at step si:

@@ -33,11 +33,15 @@ __device__ unsigned long long g_phase_cycles[16];
 __device__ unsigned long long g_stage_cycles[16];
 #define STAGE_DECL long long sg_t_ = clock64()
 #define STAGE(i) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_stage_cycles[i], (unsigned long long)(n_ - sg_t_)); sg_t_ = n_; } } while (0)
+#define DSTAGE_DECL long long ds_t_ = clock64()
+#define DSTAGE(i) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_stage_cycles[12 + (i)], (unsigned long long)(n_ - ds_t_)); ds_t_ = n_; } } while (0)
 #define RSTAGE_DECL long long rs_t_ = clock64()
 #define RSTAGE(i) do { if (lane == 0) { const long long n_ = clock64(); atomicAdd(&g_stage_cycles[9 + (i)], (unsigned long long)(n_ - rs_t_)); rs_t_ = n_; } } while (0)
 #else
 #define RSTAGE_DECL
 #define RSTAGE(i)
+#define DSTAGE_DECL
+#define DSTAGE(i)
 #define STAGE_DECL
 #define STAGE(i)
 #define PHASE_DECL
@@ -106,6 +110,7 @@ struct GiCfg {
     static constexpr int RP = RPW * NW;                      // padded rows
     static constexpr int CS = (NVMAX + 32) / 32;             // column slots per lane (one spare column)
     static constexpr int CP = CS * 32;                       // padded columns
+    static constexpr int SP = (NVMAX > 96) ? 8 : 3;          // partial sums per row of a packed symv (long horizons: H in L2)
     static constexpr int CSR = (CSR_ < 0 || CSR_ > CS) ? CS : CSR_;   // column slots held in registers ...
     static constexpr int CSS = CS - CSR;                     // ... and in shared memory (long horizons)
     static constexpr int RH = (RPW <= 8) ? 8 : (RPW <= 16 ? 16 : 32);   // reduce-scatter width
@@ -152,7 +157,7 @@ struct GiSm {
     double nvec[G::KB][G::RP];         // per-warp rows of the normals of the block's constraints
     double zrow[G::RP];                // per-warp reduced z
     double xs0[G::RP];                 // x as the block's search saw it (own rows per warp)
-    double wpart[3][G::RP];            // symv partials
+    double wpart[G::SP][G::RP];        // symv partials
     double dvec[G::RP];                // LDL' pivots
     double red_val[2][G::NW];
     unsigned long long red_key[2][G::NW * G::KB];   // per-warp top-KB violations (dkey) ...
@@ -227,18 +232,40 @@ struct GiOps {
     // rowv = Hp * v (+ addv) for this warp's rows; v full length in shared; one barrier inside
     __device__ __forceinline__ static void symv_to_rowv(SM& S, const double* v, const double* addv, int nV) {
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row0 = warp * RPW;
-        const int CH = (nV + 2) / 3;
-        for (int t = tid; t < 3 * nV; t += NT) {
+        constexpr int SP = G::SP;
+        const int CH = (nV + SP - 1) / SP;
+        for (int t = tid; t < SP * nV; t += NT) {
             const int pt = t / nV, i = t - pt * nV;
             const int j0 = pt * CH, j1 = (j0 + CH < nV) ? j0 + CH : nV;
             double acc = 0.0;
-            for (int j = j0; j < j1; ++j) acc += ((j <= i) ? S.hp()[G::hp(i, j)] : S.hp()[G::hp(j, i)]) * v[j];
+            if (SP == 3) {
+                for (int j = j0; j < j1; ++j) acc += ((j <= i) ? S.hp()[G::hp(i, j)] : S.hp()[G::hp(j, i)]) * v[j];
+            } else {
+                // packed H in the L2 slab: keep several independent loads in flight
+                double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                const double* H = S.hp();
+                int j = j0;
+                for (; j + 3 < j1; j += 4) {
+                    const double h0 = (j <= i) ? H[G::hp(i, j)] : H[G::hp(j, i)];
+                    const double h1 = (j + 1 <= i) ? H[G::hp(i, j + 1)] : H[G::hp(j + 1, i)];
+                    const double h2 = (j + 2 <= i) ? H[G::hp(i, j + 2)] : H[G::hp(j + 2, i)];
+                    const double h3 = (j + 3 <= i) ? H[G::hp(i, j + 3)] : H[G::hp(j + 3, i)];
+                    acc = fma(h0, v[j], acc); a1 = fma(h1, v[j + 1], a1); a2 = fma(h2, v[j + 2], a2); a3 = fma(h3, v[j + 3], a3);
+                }
+                for (; j < j1; ++j) acc += ((j <= i) ? H[G::hp(i, j)] : H[G::hp(j, i)]) * v[j];
+                acc += a1 + a2 + a3;
+            }
             S.wpart[pt][i] = acc;
         }
         __syncthreads();
         if (lane < RPW) {
             const int i = row0 + lane;
-            if (i < nV) S.rowv[i] = S.wpart[0][i] + S.wpart[1][i] + S.wpart[2][i] + (addv ? addv[i] : 0.0);
+            if (i < nV) {
+                double acc = S.wpart[0][i];
+#pragma unroll
+                for (int pt = 1; pt < SP; ++pt) acc += S.wpart[pt][i];
+                S.rowv[i] = acc + (addv ? addv[i] : 0.0);
+            }
         }
         __syncwarp();
     }
@@ -381,6 +408,7 @@ struct GiOps {
         // drop working-set column l: K1 <- K1 + k r'^T with r' = -K1' H k / k'Hk (k = column l), the freed
         // direction k / sqrt(k'Hk) joins J2 as column q-1, column q-1 of K1 moves into slot l
         auto drop_column = [&](int l) {
+            DSTAGE_DECL;
             const int ls = l >> 5, ll = l & 31;
             if (lane == ll) {
 #pragma unroll
@@ -391,12 +419,15 @@ struct GiOps {
                     }
             }
             __syncthreads();                                 // k = M[:, l] visible block-wide
+            DSTAGE(0);
             symv_to_rowv(S, S.colk[1], nullptr, nV);         // rowv = H k   (barrier inside)
+            DSTAGE(1);
             double kw = 0.0;
             if (lane < RPW && row0 + lane < nV) kw = S.colk[1][row0 + lane] * S.rowv[row0 + lane];
             kw = warp_sum_d(kw);
             double rp[CS], kHk;
             matvec_T(S, m, ybuf, S.rowv, kw, rp, kHk);       // rp_j = M[:,j]' (H k), kHk piggy-backed
+            DSTAGE(2);
             const double ik = 1.0 / kHk;
             const double rs = rsqrt(kHk);
             const int q1 = q - 1, q1s = q1 >> 5, q1l = q1 & 31;
@@ -441,6 +472,7 @@ struct GiOps {
             }
             --q;
             ++st.n_drop;
+            DSTAGE(3);
         };
         while (true) {
             // P1: the KB most violated inactive constraint sides (policy evaluates its slots; one

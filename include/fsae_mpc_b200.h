@@ -201,8 +201,14 @@ int fsae_qpoases_host(fsae_ctx* ctx, int B, int nV, int nC,
  * out3 = {constraints added, constraints dropped, refresh steps}; reset != 0 clears them. */
 int fsae_debug_counters(fsae_ctx* ctx, uint64_t* out3, int reset);
 /* Select the fused kernel variant: 2 (default) = register-tiled product kernel,
- * 1 = shared-memory variant kept as an in-library cross-check.  Returns the previous value. */
+ * 1 = shared-memory variant kept as an in-library cross-check; 21 / 26 / 28 / 29 = other warp
+ * counts and block sizes of the register-tiled kernel (tests).  Returns the previous value. */
 int fsae_debug_set_kernel_version(fsae_ctx* ctx, int version);
+/* Debug taps of the fused kernel (tests): DEVICE buffers that the following fsae_ltvmpc_dev calls
+ * fill, per problem and column-major, with the condensed Hessian H [nV x nV x B]
+ * (generate_qp.m:29), the gradient g [nV x B] (generate_qp.m:30) and the initial operator of the
+ * dual active-set solve M = [e_slack | J], J'HJ = I [nV x nV x B].  NULL switches a tap off. */
+int fsae_debug_set_taps(fsae_ctx* ctx, double* d_H, double* d_g, double* d_M);
 /* Measured FP64 FMA peak of the device in TFLOP/s (FMA = 2 flops): the roofline
  * denominator for the solve kernel, which MEASURED_PEAKS.json does not carry. */
 int fsae_probe_fp64_tflops(fsae_ctx* ctx, double* tflops);

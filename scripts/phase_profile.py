@@ -52,3 +52,4 @@ print(f"kernel stages, cycles per QP (tid 0): total {stot/B:.0f}")
 for i, n in enumerate(snames):
     print(f"  {n:34s} {sg[i]/B:9.0f} cyc  {100*sg[i]/stot:5.1f}%")
 print("recursion warp phases (cycles per QP): " + ", ".join(f"ph{i+1} {sg[9+i]/B:.0f}" for i in range(4)))
+print("drop phases (cycles per QP): column+barrier %.0f, H k (symv) %.0f, M'(Hk) %.0f, update %.0f" % tuple(sg[12 + i] / B for i in range(4)))

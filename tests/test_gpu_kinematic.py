@@ -215,3 +215,59 @@ def test_other_horizons_match_golden(mpc, N):
     g = load_golden(f"kinematic_lap_fsg2019_N{N}.npz")
     r = mpc.ltvmpc_kinetmatic_curvilinear(g["x0"], c_layout(g["x_ref"]), DT, c_layout(g["x_lin"]), c_layout(g["u_lin"]))
     _check_solution(r, g)
+
+
+@pytest.mark.parametrize("model_name,N", [("kinematic", 40), ("kinematic", 20), ("kinematic", 80), ("dynamic", 40)])
+def test_fused_kernel_taps_hessian_gradient_and_operator(mpc, model_name, N):
+    """Stage-level check INSIDE the fused kernel: the Hessian it builds from the cost Gramian (one dot
+    product per entry) and the gradient equal the condense stage's H / f (which the reference's own
+    generate_qp.m pins, tests/test_reference_vectors.py), and the operator it gets from the Riccati
+    recursion + adjoint rows (no factorisation) satisfies J'HJ = I with the slack columns leading."""
+    import torch
+    import fsae_mpc_b200 as fm
+    model = fm.KINEMATIC if model_name == "kinematic" else fm.DYNAMIC
+    fx = {("kinematic", 40): "kinematic_lap_fsg2019.npz", ("kinematic", 20): "kinematic_lap_fsg2019_N20.npz",
+          ("kinematic", 80): "kinematic_lap_fsg2019_N80.npz", ("dynamic", 40): "dynamic_lap_fss2019.npz"}[(model_name, N)]
+    g = load_golden(fx)
+    B = min(6, g["x0"].shape[0])
+    NX, NU, NS = (5, 2, 1) if model_name == "kinematic" else (7, 2, 4)
+    nU, nV = NU * N, NU * N + NS
+    tid = np.full(B, 0 if model_name == "kinematic" else 1, np.int32)
+    pid = np.zeros(B, np.int32)
+    if model_name == "dynamic":
+        mpc.set_params(3, fm.default_params(fm.DYNAMIC))
+        pid[:] = 3
+    x0, xr, xl, ul = g["x0"][:B], c_layout(g["x_ref"][:B]), c_layout(g["x_lin"][:B]), c_layout(g["u_lin"][:B])
+    ref = mpc.condense(model, x0, xr, DT, xl, ul, track_id=tid, param_id=pid)
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (x0, xr, xl, ul, tid, pid)]
+    o = dict(u_opt=torch.empty((B, nU), dtype=torch.float64, device=dev), x_opt=torch.empty((B, NX * N), dtype=torch.float64, device=dev),
+             exitflag=torch.empty(B, dtype=torch.int32, device=dev), fval=torch.empty(B, dtype=torch.float64, device=dev),
+             slack_opt=torch.empty((B, NS), dtype=torch.float64, device=dev))
+    tH = torch.zeros((B, nV, nV), dtype=torch.float64, device=dev)
+    tg = torch.zeros((B, nV), dtype=torch.float64, device=dev)
+    tM = torch.zeros((B, nV, nV), dtype=torch.float64, device=dev)
+    ptrs = dict(x0=d[0].data_ptr(), x_ref=d[1].data_ptr(), x_lin=d[2].data_ptr(), u_lin=d[3].data_ptr(), track_id=d[4].data_ptr(),
+                param_id=d[5].data_ptr(), **{k: v.data_ptr() for k, v in o.items()})
+    mpc.set_taps(tH.data_ptr(), tg.data_ptr(), tM.data_ptr())
+    try:
+        mpc.ltvmpc_dev(model, B, N, DT, ptrs, stream=mpc.stream)
+        torch.cuda.synchronize()
+    finally:
+        mpc.set_taps(0, 0, 0)
+    H = tH.cpu().numpy().transpose(0, 2, 1)          # column-major per problem
+    M = tM.cpu().numpy().transpose(0, 2, 1)
+    gv = tg.cpu().numpy()
+    Href = np.asarray(ref["H"]).reshape(B, nV, nV)
+    fref = np.asarray(ref["f"]).reshape(B, nV)
+    for b in range(B):
+        hs = np.abs(Href[b]).max()
+        assert np.abs(H[b][:nU, :nU] - Href[b][:nU, :nU]).max() <= 1e-11 * hs, (b, "H")
+        assert np.abs(H[b] - H[b].T).max() == 0.0
+        assert np.abs(gv[b] - fref[b]).max() <= 1e-10 * (1.0 + np.abs(fref[b]).max()), (b, "g")
+        J = M[b][:nU, NS:]
+        E = J.T @ Href[b][:nU, :nU] @ J - np.eye(nU)
+        assert np.abs(E).max() <= 1e-9, (b, "J'HJ - I", np.abs(E).max())
+        # slack columns lead: unit vectors on the slack rows, nothing else
+        assert np.array_equal(M[b][:, :NS], np.eye(nV)[:, nU:])
+        assert np.abs(M[b][nU:, NS:]).max() == 0.0
