@@ -37,7 +37,7 @@ struct SmemV2 {
     static constexpr bool LONG = G::CSS > 0;
     static constexpr int NBF = LONG ? C::NCR : C::NREAL;                    // B_bar rows in shared memory
     __host__ __device__ static constexpr int bfc(int c) { return LONG ? c : C::cons_real(c); }   // row of constraint state c
-    static constexpr size_t SLAB = LONG ? (size_t)C::NREAL * D::NPK + D::HP : 0;                  // doubles per problem
+    static constexpr size_t SLAB = LONG ? (size_t)C::NREAL * D::NPK + (size_t)D::nV * D::nV : 0;  // doubles per problem (B_bar rows + full H)
     alignas(16) double Bf[NBF * D::NPK];        // packed B_bar rows (kept to the end)
     GiSm<G, D::NSLOT, LONG> gi;                 // x, g, packed H, working set, core scratch
     double B1[D::NX * D::NU];
@@ -228,6 +228,142 @@ struct MpcProb {
     __device__ __forceinline__ bool is_unit(int pslot) const { return pslot < D::nV; }
 };
 
+// The two backward recursions over the horizon (s = N-1 .. 0), run by ONE warp each (or both by the same
+// warp when the CTA has only four):
+//   DO_W  Gramian  W_s = Q + A_s' W_{s+1} A_s                       -> G_s = B' W_{s+1}   (entries of H)
+//   DO_P  Riccati  P_s = Q + A_s' P_{s+1} A_s - S' Lambda^-1 S,  Lambda = R + B' P_{s+1} B,
+//                  S = B' P_{s+1} A_s,  K_s = -Lambda^-1 S           -> J (adjoint rows), stage published
+// The Riccati identity  u'(B_bar' Qbar B_bar + Rbar) u = sum_s |Lambda_s^(1/2) (u_s - K_s x_s)|^2
+// makes J = T^-1 / sqrt 2 (J'HJ = I) the closed-loop response to unit "innovations":
+// u_s = K_s x_s + Lambda_s^(-T/2) v_s.  No dense factorisation of H is needed.
+template <bool DO_W, bool DO_P, class Model, int N, class S_t>
+__device__ __forceinline__ void horizon_recursions(S_t& S, const fsae_params& P) {
+    using D = Dims<Model, N>;
+    using C = Cons<Model>;
+    constexpr int NX = D::NX, NU = D::NU;
+    const int lane = threadIdx.x & 31;
+    {
+        static_assert(NU == 2, "2 x 2 Lambda blocks are inverted in closed form");
+        constexpr int NN = NX * NX, NB = NU * NX, NR_ = C::NREAL;
+        double* Wb = S.wgram;               // [2][NN]
+        double* Pb = S.wgram + 2 * NN;      // [2][NN]
+        double* TW = S.wgram + 4 * NN;      // W A
+        double* TP = S.wgram + 5 * NN;      // P A
+        double* BP = S.wgram + 6 * NN;      // B'P            [NU][NX]
+        double* Sm = BP + NB;               // S = B'P A      [NU][NX]
+        double* Kx = Sm + NB;               // K              [NU][NX]
+        for (int e = lane; e < NN; e += 32) {
+            const double v = (e / NX == e % NX) ? P.Q_terminal[e / NX] : 0.0;
+            if (DO_W) Wb[e] = v;
+            if (DO_P) Pb[e] = v;
+        }
+        __syncwarp();
+        int cur = 0;
+        RSTAGE_DECL;
+        // Three warp-synchronous phases per stage; every lane runs the same instruction stream on its own
+        // entry (indices clamped, stores predicated), the dot products of a phase are independent chains.
+        for (int st = N - 1; st >= 0; --st) {
+            const double* W = Wb + cur * NN;
+            const double* Pm = Pb + cur * NN;
+            const double* As = S.Ad + st * NR_ * NX;          // rows of the real states; integrator rows are unit rows
+            // phase 1: W A, P A (entry (i, j));  B'P, G_s = B'W (entry (c = i, j), i < NU)
+            for (int e0 = 0; e0 < NN; e0 += 32) {
+                const int e = (e0 + lane < NN) ? e0 + lane : 0;
+                const int i = e / NX, j = e - i * NX, c = i < NU ? i : NU - 1;
+                double tw = (DO_W && j >= NR_) ? W[i * NX + j] : 0.0, tp = (DO_P && j >= NR_) ? Pm[i * NX + j] : 0.0, bp = 0.0, wb = 0.0;
+#pragma unroll
+                for (int l = 0; l < NX; ++l) {
+                    const double bl = S.B1[l * NU + c];
+                    if (DO_P) bp = fma(bl, Pm[l * NX + j], bp);
+                    if (DO_W) wb = fma(bl, W[l * NX + j], wb);
+                    if (l < NR_) {
+                        const double al = As[l * NX + j];
+                        if (DO_W) tw = fma(W[i * NX + l], al, tw);
+                        if (DO_P) tp = fma(Pm[i * NX + l], al, tp);
+                    }
+                }
+                if (e0 + lane < NN) { if (DO_W) TW[e] = tw; if (DO_P) TP[e] = tp; }
+                if (e0 + lane < NB) { if (DO_P) BP[e] = bp; if (DO_W) S.Gs[(st * NU + c) * NX + j] = wb; }
+            }
+            __syncwarp();
+            RSTAGE(0);
+            // phase 2 (lane = (c, j), c < NU): S = (B'P) A column j, Lambda = R + (B'P) B, K = -Lambda^-1 S
+            if (DO_P) {
+                const int e = lane < NB ? lane : 0;
+                const int c = e / NX, j = e - c * NX;
+                double s0 = (j >= NR_) ? BP[j] : 0.0, s1 = (j >= NR_) ? BP[NX + j] : 0.0;
+                double la = P.R[0], lb = 0.0, ld = P.R[1];
+#pragma unroll
+                for (int l = 0; l < NX; ++l) {
+                    const double b0 = BP[l], b1 = BP[NX + l];
+                    la = fma(b0, S.B1[l * NU + 0], la);
+                    lb = fma(b0, S.B1[l * NU + 1], lb);
+                    ld = fma(b1, S.B1[l * NU + 1], ld);
+                    if (l < NR_) {
+                        const double al = As[l * NX + j];
+                        s0 = fma(b0, al, s0);
+                        s1 = fma(b1, al, s1);
+                    }
+                }
+                const double rdet = __drcp_rn(fma(la, ld, -lb * lb));
+                const double kv = (c == 0) ? (lb * s1 - ld * s0) * rdet : (lb * s0 - la * s1) * rdet;
+                if (lane < NB) {
+                    Sm[e] = (c == 0) ? s0 : s1;
+                    Kx[e] = kv;
+                    S.Kc[(st * NU + c) * NX + j] = kv;
+                }
+                if (lane < 3) S.Lam3[st * 3 + lane] = (lane == 0) ? la : (lane == 1 ? lb : ld);
+            }
+            if (DO_P) {
+                __syncwarp();
+                if (lane == 0) {                   // K_st is in shared memory: publish the stage
+                    __threadfence_block();
+                    *(volatile int*)&S.prog = st;
+                }
+            }
+            RSTAGE(1);
+            if (st == 0) break;
+            // phase 3: W' = Q + A'(W A),  P' = Q + A'(P A) + S'K
+            double* Wn = Wb + (cur ^ 1) * NN;
+            double* Pn = Pb + (cur ^ 1) * NN;
+            for (int e0 = 0; e0 < NN; e0 += 32) {
+                const int e = (e0 + lane < NN) ? e0 + lane : 0;
+                const int i = e / NX, j = e - i * NX;
+                const double qd = (i == j) ? P.Q[i] : 0.0;
+                double aw = qd + ((DO_W && i >= NR_) ? TW[i * NX + j] : 0.0);
+                double ap = qd + ((DO_P && i >= NR_) ? TP[i * NX + j] : 0.0);
+                double sk = 0.0;
+#pragma unroll
+                for (int l = 0; l < NR_; ++l) {
+                    const double al = As[l * NX + i];
+                    if (DO_W) aw = fma(al, TW[l * NX + j], aw);
+                    if (DO_P) ap = fma(al, TP[l * NX + j], ap);
+                }
+                if (DO_P) {
+#pragma unroll
+                    for (int c = 0; c < NU; ++c) sk = fma(Sm[c * NX + i], Kx[c * NX + j], sk);
+                }
+                if (e0 + lane < NN) { if (DO_W) Wn[e] = aw; if (DO_P) Pn[e] = ap + sk; }
+            }
+            __syncwarp();
+            RSTAGE(2);
+            cur ^= 1;
+        }
+        // Lambda_s^(-T/2) / sqrt 2 for every stage (off the recursion's critical path).  Lambda = G G',
+        // G = [l11 0; l21 l22]:  G^-T = [1/l11  -l21/(l11 l22); 0  1/l22]
+        for (int st = lane; DO_P && st < N; st += 32) {
+            const double la = S.Lam3[st * 3], lb = S.Lam3[st * 3 + 1], ld = S.Lam3[st * 3 + 2];
+            const double i11 = rsqrt(la), l21 = lb * i11;
+            const double i22 = rsqrt(fma(-l21, l21, ld));
+            const double r2 = 0.70710678118654752440;
+            S.Wi[st * 4 + 0] = r2 * i11;
+            S.Wi[st * 4 + 1] = -r2 * l21 * i11 * i22;
+            S.Wi[st * 4 + 2] = 0.0;
+            S.Wi[st * 4 + 3] = r2 * i22;
+        }
+    }
+}
+
 template <class Model, int N, int MINB, int NW_ = 8, int KB_ = 1, int CSR_ = -1>
 __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchArgs a) {
     using D = Dims<Model, N>;
@@ -329,8 +465,9 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     // follow the recursion stage by stage (adjoint rows of J, below); all meet before the tiles
     // are filled.  With four warps the recursion shares the free-response warp and nothing overlaps.
     static_assert(NW >= 4, "stage map: three chain warps + the free-response warp");
+    // (Running the two recursions on two warps was measured: no gain -- one worker warp fewer, same critical path.)
     constexpr bool OVL = NW >= 5;
-    constexpr int GW = OVL ? 3 : NW - 1;
+    constexpr int GW = OVL ? 3 : NW - 1;                         // recursion warp
     constexpr int WNT = OVL ? NT - 32 : NT;                      // worker threads
     const bool worker = !OVL || warp != GW;
     const int wtid = (OVL && warp > GW) ? tid - 32 : tid;        // worker index
@@ -338,129 +475,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
         if (OVL) asm volatile("bar.sync 1, %0;" ::"r"(WNT) : "memory");
         else __syncthreads();
     };
-    if (warp == GW) {
-        // Two backward recursions share the pass (s = N-1 .. 0):
-        //   Gramian  W_s = Q + A_s' W_{s+1} A_s                      -> G_s = B' W_{s+1}   (entries of H)
-        //   Riccati  P_s = Q + A_s' P_{s+1} A_s - S' Lambda^-1 S,  Lambda = R + B' P_{s+1} B,
-        //            S = B' P_{s+1} A_s,  K_s = -Lambda^-1 S
-        // The Riccati identity  u'(B_bar' Qbar B_bar + Rbar) u = sum_s |Lambda_s^(1/2) (u_s - K_s x_s)|^2
-        // makes J = T^-1 / sqrt 2 (J'HJ = I) the closed-loop response to unit "innovations":
-        // u_s = K_s x_s + Lambda_s^(-T/2) v_s.  No dense factorisation of H is needed.
-        static_assert(NU == 2, "2 x 2 Lambda blocks are inverted in closed form");
-        constexpr int NN = NX * NX, NB = NU * NX, NR_ = C::NREAL;
-        double* Wb = S.wgram;               // [2][NN]
-        double* Pb = S.wgram + 2 * NN;      // [2][NN]
-        double* TW = S.wgram + 4 * NN;      // W A
-        double* TP = S.wgram + 5 * NN;      // P A
-        double* BP = S.wgram + 6 * NN;      // B'P            [NU][NX]
-        double* Sm = BP + NB;               // S = B'P A      [NU][NX]
-        double* Kx = Sm + NB;               // K              [NU][NX]
-        for (int e = lane; e < NN; e += 32) {
-            const double v = (e / NX == e % NX) ? P.Q_terminal[e / NX] : 0.0;
-            Wb[e] = v;
-            Pb[e] = v;
-        }
-        __syncwarp();
-        int cur = 0;
-        RSTAGE_DECL;
-        // Three warp-synchronous phases per stage; every lane runs the same instruction stream on its own
-        // entry (indices clamped, stores predicated), the dot products of a phase are independent chains.
-        for (int st = N - 1; st >= 0; --st) {
-            const double* W = Wb + cur * NN;
-            const double* Pm = Pb + cur * NN;
-            const double* As = S.Ad + st * NR_ * NX;          // rows of the real states; integrator rows are unit rows
-            // phase 1: W A, P A (entry (i, j));  B'P, G_s = B'W (entry (c = i, j), i < NU)
-            for (int e0 = 0; e0 < NN; e0 += 32) {
-                const int e = (e0 + lane < NN) ? e0 + lane : 0;
-                const int i = e / NX, j = e - i * NX, c = i < NU ? i : NU - 1;
-                double tw = (j >= NR_) ? W[i * NX + j] : 0.0, tp = (j >= NR_) ? Pm[i * NX + j] : 0.0, bp = 0.0, wb = 0.0;
-#pragma unroll
-                for (int l = 0; l < NX; ++l) {
-                    const double bl = S.B1[l * NU + c];
-                    bp = fma(bl, Pm[l * NX + j], bp);
-                    wb = fma(bl, W[l * NX + j], wb);
-                    if (l < NR_) {
-                        const double al = As[l * NX + j];
-                        tw = fma(W[i * NX + l], al, tw);
-                        tp = fma(Pm[i * NX + l], al, tp);
-                    }
-                }
-                if (e0 + lane < NN) { TW[e] = tw; TP[e] = tp; }
-                if (e0 + lane < NB) { BP[e] = bp; S.Gs[(st * NU + c) * NX + j] = wb; }
-            }
-            __syncwarp();
-            RSTAGE(0);
-            // phase 2 (lane = (c, j), c < NU): S = (B'P) A column j, Lambda = R + (B'P) B, K = -Lambda^-1 S
-            {
-                const int e = lane < NB ? lane : 0;
-                const int c = e / NX, j = e - c * NX;
-                double s0 = (j >= NR_) ? BP[j] : 0.0, s1 = (j >= NR_) ? BP[NX + j] : 0.0;
-                double la = P.R[0], lb = 0.0, ld = P.R[1];
-#pragma unroll
-                for (int l = 0; l < NX; ++l) {
-                    const double b0 = BP[l], b1 = BP[NX + l];
-                    la = fma(b0, S.B1[l * NU + 0], la);
-                    lb = fma(b0, S.B1[l * NU + 1], lb);
-                    ld = fma(b1, S.B1[l * NU + 1], ld);
-                    if (l < NR_) {
-                        const double al = As[l * NX + j];
-                        s0 = fma(b0, al, s0);
-                        s1 = fma(b1, al, s1);
-                    }
-                }
-                const double rdet = __drcp_rn(fma(la, ld, -lb * lb));
-                const double kv = (c == 0) ? (lb * s1 - ld * s0) * rdet : (lb * s0 - la * s1) * rdet;
-                if (lane < NB) {
-                    Sm[e] = (c == 0) ? s0 : s1;
-                    Kx[e] = kv;
-                    S.Kc[(st * NU + c) * NX + j] = kv;
-                }
-                if (lane < 3) S.Lam3[st * 3 + lane] = (lane == 0) ? la : (lane == 1 ? lb : ld);
-            }
-            __syncwarp();
-            if (lane == 0) {                       // K_st and G_st are in shared memory: publish the stage
-                __threadfence_block();
-                *(volatile int*)&S.prog = st;
-            }
-            RSTAGE(1);
-            if (st == 0) break;
-            // phase 3: W' = Q + A'(W A),  P' = Q + A'(P A) + S'K
-            double* Wn = Wb + (cur ^ 1) * NN;
-            double* Pn = Pb + (cur ^ 1) * NN;
-            for (int e0 = 0; e0 < NN; e0 += 32) {
-                const int e = (e0 + lane < NN) ? e0 + lane : 0;
-                const int i = e / NX, j = e - i * NX;
-                const double qd = (i == j) ? P.Q[i] : 0.0;
-                double aw = qd + ((i >= NR_) ? TW[i * NX + j] : 0.0);
-                double ap = qd + ((i >= NR_) ? TP[i * NX + j] : 0.0);
-                double sk = 0.0;
-#pragma unroll
-                for (int l = 0; l < NR_; ++l) {
-                    const double al = As[l * NX + i];
-                    aw = fma(al, TW[l * NX + j], aw);
-                    ap = fma(al, TP[l * NX + j], ap);
-                }
-#pragma unroll
-                for (int c = 0; c < NU; ++c) sk = fma(Sm[c * NX + i], Kx[c * NX + j], sk);
-                if (e0 + lane < NN) { Wn[e] = aw; Pn[e] = ap + sk; }
-            }
-            __syncwarp();
-            RSTAGE(2);
-            cur ^= 1;
-        }
-        // Lambda_s^(-T/2) / sqrt 2 for every stage (off the recursion's critical path).  Lambda = G G',
-        // G = [l11 0; l21 l22]:  G^-T = [1/l11  -l21/(l11 l22); 0  1/l22]
-        for (int st = lane; st < N; st += 32) {
-            const double la = S.Lam3[st * 3], lb = S.Lam3[st * 3 + 1], ld = S.Lam3[st * 3 + 2];
-            const double i11 = rsqrt(la), l21 = lb * i11;
-            const double i22 = rsqrt(fma(-l21, l21, ld));
-            const double r2 = 0.70710678118654752440;
-            S.Wi[st * 4 + 0] = r2 * i11;
-            S.Wi[st * 4 + 1] = -r2 * l21 * i11 * i22;
-            S.Wi[st * 4 + 2] = 0.0;
-            S.Wi[st * 4 + 3] = r2 * i22;
-        }
-    }
+    if (warp == GW) horizon_recursions<true, true, Model, N>(S, P);
     if (warp == NW - 1) {
         if (lane == 0) {
             double xp[NX], xn[NX];
@@ -763,7 +778,13 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
                 if (i == j) h += 2.0 * P.R[ci];
             }
             if (gH) { gH[(size_t)j * nV + i] = h; gH[(size_t)i * nV + j] = h; }
-            S.gi.hp()[D::hp(i, j)] = (i >= nU) ? (i == j ? P.flat_eps : 0.0) : h;
+            const double hv = (i >= nU) ? (i == j ? P.flat_eps : 0.0) : h;
+            if (LONG) {                             // full symmetric matrix in the L2 slab: coalesced symv's
+                S.gi.hp()[(size_t)i * nV + j] = hv;
+                S.gi.hp()[(size_t)j * nV + i] = hv;
+            } else {
+                S.gi.hp()[D::hp(i, j)] = hv;
+            }
         }
     }
     if (a.dbg_g) {

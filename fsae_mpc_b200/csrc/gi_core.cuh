@@ -149,7 +149,8 @@ struct GiSm {
     alignas(16) double x[G::RP];
     double g[G::RP];
     double Hp[HPG ? 2 : G::HP];        // packed lower triangle of H (drops, refresh, fval) ...
-    double* hpg;                       // ... or, for long horizons, a per-problem global (L2-resident) slab
+    double* hpg;                       // ... or, for long horizons, the FULL symmetric H in a per-problem global (L2-resident) slab
+    static constexpr bool HFULL = HPG;
     __device__ __forceinline__ double* hp() { return HPG ? hpg : Hp; }
     double ypart[G::YB][G::NW][G::CP]; // cross-warp partial sums of M'v (double-buffered; one buffer per block member)
     double colk[2][G::RP];             // column broadcast (factorisation / column q / drop column)
@@ -238,22 +239,23 @@ struct GiOps {
             const int pt = t / nV, i = t - pt * nV;
             const int j0 = pt * CH, j1 = (j0 + CH < nV) ? j0 + CH : nV;
             double acc = 0.0;
-            if (SP == 3) {
+            if (!SM::HFULL) {
                 for (int j = j0; j < j1; ++j) acc += ((j <= i) ? S.hp()[G::hp(i, j)] : S.hp()[G::hp(j, i)]) * v[j];
             } else {
-                // packed H in the L2 slab: keep several independent loads in flight
-                double a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                const double* H = S.hp();
-                int j = j0;
-                for (; j + 3 < j1; j += 4) {
-                    const double h0 = (j <= i) ? H[G::hp(i, j)] : H[G::hp(j, i)];
-                    const double h1 = (j + 1 <= i) ? H[G::hp(i, j + 1)] : H[G::hp(j + 1, i)];
-                    const double h2 = (j + 2 <= i) ? H[G::hp(i, j + 2)] : H[G::hp(j + 2, i)];
-                    const double h3 = (j + 3 <= i) ? H[G::hp(i, j + 3)] : H[G::hp(j + 3, i)];
-                    acc = fma(h0, v[j], acc); a1 = fma(h1, v[j + 1], a1); a2 = fma(h2, v[j + 2], a2); a3 = fma(h3, v[j + 3], a3);
+                // full symmetric H in the L2 slab, read by columns (H[j][i] = H[i][j]): consecutive threads read
+                // consecutive addresses; four independent loads in flight
+                const double* H = S.hp() + i;
+                double a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = 0.0;
+                for (int j = j0; j < j1; j += 8) {
+                    double h[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) h[u] = (j + u < j1) ? H[(size_t)(j + u) * nV] : 0.0;     // eight L2 loads in flight
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a[u] = fma(h[u], (j + u < j1) ? v[j + u] : 0.0, a[u]);
                 }
-                for (; j < j1; ++j) acc += ((j <= i) ? H[G::hp(i, j)] : H[G::hp(j, i)]) * v[j];
-                acc += a1 + a2 + a3;
+                acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
             }
             S.wpart[pt][i] = acc;
         }
