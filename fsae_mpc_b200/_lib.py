@@ -68,6 +68,8 @@ SIGNATURES = {
                           + [_dp, _dp, _ip, _ip, _dp, _bp, _bp]),
     "fsae_debug_counters": (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.c_int]),
     "fsae_debug_set_kernel_version": (C.c_int, [_ctx, C.c_int]),
+    "fsae_obtain_reference_host": (C.c_int, [_ctx, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_double,
+                                             C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     "fsae_debug_set_taps": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fsae_probe_fp64_tflops": (C.c_int, [_ctx, C.POINTER(C.c_double)]),
 }

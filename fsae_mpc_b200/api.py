@@ -147,6 +147,21 @@ class FsaeMpc:
                     "fsae_linearise_host")
         return A.transpose(0, 1, 3, 2), Bm.transpose(0, 1, 3, 2), d
 
+    def obtain_reference(self, plan_x, ds, plan_t, s0, dt, N_t):
+        """util/obtain_reference.m for a batch of vehicles: plan_x (N_s, 8) [the planner's x, one row per
+        arclength sample], plan_t (N_s,), s0 (B,) -> x_ref (B, N_t, 7) in the C-ABI layout."""
+        plan_x = np.ascontiguousarray(plan_x, dtype=np.float64).reshape(-1)
+        plan_t = np.ascontiguousarray(plan_t, dtype=np.float64).reshape(-1)
+        s0 = np.ascontiguousarray(np.atleast_1d(s0), dtype=np.float64)
+        N_s, B = plan_t.size, s0.size
+        if plan_x.size != 8 * N_s:
+            raise ValueError("plan_x must hold 8 values per arclength sample")
+        out = np.empty((B, int(N_t), 7), dtype=np.float64)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        self._check(self._lib.fsae_obtain_reference_host(self._ctx, dp(plan_x), dp(plan_t), N_s, float(ds), dp(s0), B,
+                                                         float(dt), int(N_t), dp(out)), "fsae_obtain_reference_host")
+        return out
+
     def condense(self, model, x0, x_ref, dt, x_lin, u_lin, track_id=None, param_id=None):
         """sequential_integration.m + *_state_constraints.m + generate_qp.m.  Returns a dict of
         per-problem matrices in natural (row, col) indexing."""

@@ -14,6 +14,7 @@
 #include "probe.cuh"
 #include "dense_qp.cuh"
 #include "closed_loop.cuh"
+#include "reference.cuh"
 
 using namespace fsae;
 
@@ -231,6 +232,30 @@ extern "C" int fsae_interpolate_curvature_host(fsae_ctx* ctx, int track_id, cons
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(kappa_out, ctx->out[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSAE_OK;
+}
+
+extern "C" int fsae_obtain_reference_host(fsae_ctx* ctx, const double* plan_x, const double* plan_t, int N_s, double ds,
+                                          const double* s0, int B, double dt, int N_t, double* x_ref) {
+    if (!ctx || !plan_x || !plan_t || !s0 || !x_ref || N_s < 1 || B < 0 || N_t < 1 || !(ds > 0.0) || !(dt > 0.0)) return FSAE_ERR_ARG;
+    if (B == 0) return FSAE_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t bx = (size_t)8 * N_s * sizeof(double), bt = (size_t)N_s * sizeof(double), bs = (size_t)B * sizeof(double);
+    const size_t bo = (size_t)7 * N_t * B * sizeof(double);
+    CK(ctx->in[0].reserve(bx));
+    CK(ctx->in[1].reserve(bt));
+    CK(ctx->in[2].reserve(bs));
+    CK(ctx->out[0].reserve(bo));
+    CK(cudaMemcpyAsync(ctx->in[0].p, plan_x, bx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->in[1].p, plan_t, bt, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->in[2].p, s0, bs, cudaMemcpyHostToDevice, ctx->stream));
+    fsae::obtain_reference_kernel<<<(unsigned)((B + 127) / 128), 128, 0, ctx->stream>>>(
+        (const double*)ctx->in[0].p, (const double*)ctx->in[1].p, N_s, ds, (const double*)ctx->in[2].p, B, dt, N_t,
+        (double*)ctx->out[0].p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(x_ref, ctx->out[0].p, bo, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return FSAE_OK;
 }

@@ -107,6 +107,15 @@ int fsae_set_params(fsae_ctx* ctx, int id, const fsae_params* p);
 int fsae_set_track(fsae_ctx* ctx, int track_id, const double* x_spline, const double* y_spline,
                    int n_seg, double dl);
 
+/* ---- util/obtain_reference.m:1-50 (call site main.m:115), batched over vehicles ----------
+ * Re-parameterises a planned lap from arclength to time: plan_x [8 x N_s] column-major
+ * (n, mu, x_d, y_d, theta_d, delta, a, delta_d at every ds metres -- the `x` the reference's
+ * minimum-time planner returns), plan_t [N_s] the time spent in each segment.  Vehicle b starts at
+ * arclength s0[b]; x_ref [7 x N_t x B] (s, n, mu, x_d, y_d, theta_d, delta at dt, 2dt, .. N_t dt) is
+ * the `x_ref` argument of ltvmpc_dynamic_curvilinear.  Bit-identical to the .m file.  Host pointers. */
+int fsae_obtain_reference_host(fsae_ctx* ctx, const double* plan_x, const double* plan_t, int N_s, double ds,
+                               const double* s0, int B, double dt, int N_t, double* x_ref);
+
 /* ---- spline/interpolate_curvature.m:1-20, batched over s (host pointers) -------- */
 int fsae_interpolate_curvature_host(fsae_ctx* ctx, int track_id, const double* s, int64_t n,
                                     double* kappa_out);

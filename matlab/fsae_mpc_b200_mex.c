@@ -64,6 +64,16 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         const int n = (int)mxGetM(prhs[3]);
         check(c, fsae_set_track(c, (int)mxGetScalar(prhs[2]), mxGetPr(prhs[3]), mxGetPr(prhs[4]), n,
                                 mxGetScalar(prhs[5])), "set_track");
+    } else if (!strcmp(cmd, "obtain_reference")) {
+        /* (h, x [8*N_s], ds, N_s, t [N_s], s0 [1 x B], dt, N_t) -> x_ref [7 x N_t x B]  -- util/obtain_reference.m:1 */
+        if (nrhs != 9) mexErrMsgTxt("obtain_reference: 8 arguments");
+        const int N_s = (int)mxGetScalar(prhs[4]), N_t = (int)mxGetScalar(prhs[8]);
+        const int B = (int)mxGetNumberOfElements(prhs[6]);
+        mwSize dims[3] = {7, (mwSize)N_t, (mwSize)B};
+        plhs[0] = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        check(c, fsae_obtain_reference_host(c, mxGetPr(prhs[2]), mxGetPr(prhs[5]), N_s, mxGetScalar(prhs[3]),
+                                            mxGetPr(prhs[6]), B, mxGetScalar(prhs[7]), N_t, mxGetPr(plhs[0])),
+              "obtain_reference");
     } else if (!strcmp(cmd, "ltvmpc")) {
         /* (h, model, x0, x_ref, dt, x_lin, u_lin [, track_id, param_id]) */
         if (nrhs < 8) mexErrMsgTxt("ltvmpc: 7+ arguments");

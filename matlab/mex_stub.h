@@ -23,5 +23,6 @@ int mxIsEmpty(const mxArray*);
 int mxGetString(const mxArray*, char*, mwSize);
 mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
 mxArray* mxCreateNumericMatrix(mwSize, mwSize, mxClassID, mxComplexity);
+mxArray* mxCreateNumericArray(mwSize, const mwSize*, mxClassID, mxComplexity);
 void mexErrMsgTxt(const char*);
 #endif

@@ -61,6 +61,33 @@ def run(model, track, fixture, picks):
     print("reference functions executed:", ", ".join(sorted(ml.calls)))
 
 
+
+
+def run_obtain_reference():
+    """util/obtain_reference.m executed on synthetic plans (the reference's own plan comes from its IPOPT
+    minimum-time planner, a Windows MEX binary): smooth lap-like state samples, segment times between a
+    fraction of dt and several dt, starting points before, inside and beyond one lap."""
+    ml = Matlab([R + "/util"])
+    rng = np.random.default_rng(5)
+    cases = []
+    for N_s, ds, N_t, dt in ((50, 2.5, 40, 0.05), (300, 1.0, 40, 0.05), (128, 0.4, 80, 0.05), (64, 3.0, 20, 0.1)):
+        ph = 2 * np.pi * np.arange(N_s) / N_s
+        plan = np.zeros((8, N_s))
+        for k in range(8):
+            plan[k] = rng.normal() * np.sin((k % 3 + 1) * ph + rng.uniform(0, 6)) + 0.1 * rng.normal(size=N_s)
+        plan[2] = 12.0 + 6.0 * np.sin(ph)                       # x_d > 0
+        t = ds / plan[2] * (1.0 + 0.3 * rng.uniform(-1, 1, N_s))
+        x = plan.reshape(-1, order="F").reshape(-1, 1)
+        for s0 in (0.0, 0.37 * ds, 7.9 * ds, ds * N_s - 0.2 * ds, 1.6 * ds * N_s, float(rng.uniform(0, ds * N_s))):
+            out = ml.call("obtain_reference", x, ds, float(N_s), t.reshape(-1, 1), s0, dt, float(N_t))
+            cases.append(dict(x=x.ravel(), t=t, ds=ds, N_s=N_s, s0=s0, dt=dt, N_t=N_t, x_ref=np.asarray(out)))
+    np.savez_compressed(os.path.join(GOLD, "reference_m_obtain_reference.npz"), n=len(cases),
+                        **{f"c{i}_{k}": np.asarray(v) for i, c in enumerate(cases) for k, v in c.items()})
+    print("obtain_reference:", len(cases), "cases")
+
+
 if __name__ == "__main__":
-    run("kinematic", "fsg2019", "kinematic_lap_fsg2019.npz", [3, 20, 41, 60, 77])
-    run("dynamic", "fss2019", "dynamic_lap_fss2019.npz", [5, 23, 40])
+    if "--only-reference" not in sys.argv:
+        run("kinematic", "fsg2019", "kinematic_lap_fsg2019.npz", [3, 20, 41, 60, 77])
+        run("dynamic", "fss2019", "dynamic_lap_fss2019.npz", [5, 23, 40])
+    run_obtain_reference()

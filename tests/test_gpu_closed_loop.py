@@ -56,3 +56,27 @@ def _oracle_run(track, model, n_sim, plant0):
             x = vm.integrate_cart_dyn(x, np.array([vr, sr]), 0.005)
         hist["x"].append(x.copy())
     return hist
+
+
+def test_obtain_reference_matches_reference_m_file_bit_for_bit(mpc):
+    """fsae_obtain_reference_host (util/obtain_reference.m for a batch of vehicles) against the outputs of the
+    reference's own .m file on the committed plans, and against the oracle on a larger batch of start points."""
+    from conftest import load_golden
+    from oracle import reference as rf
+    g = load_golden("reference_m_obtain_reference.npz")
+    groups = {}
+    for i in range(int(g["n"])):
+        key = (int(g[f"c{i}_N_s"]), float(g[f"c{i}_ds"]), int(g[f"c{i}_N_t"]), float(g[f"c{i}_dt"]))
+        groups.setdefault(key, []).append(i)
+    for (N_s, ds, N_t, dt), idx in groups.items():
+        x, t = g[f"c{idx[0]}_x"], g[f"c{idx[0]}_t"]
+        s0 = np.array([float(g[f"c{i}_s0"]) for i in idx])
+        out = mpc.obtain_reference(x.reshape(N_s, 8), ds, t, s0, dt, N_t)
+        for j, i in enumerate(idx):
+            assert np.array_equal(out[j].T, g[f"c{i}_x_ref"]), (N_s, i)
+        rng = np.random.default_rng(N_s)
+        s0 = rng.uniform(-0.5 * ds * N_s, 2.5 * ds * N_s, 257)          # ragged batch, before / beyond one lap
+        out = mpc.obtain_reference(x.reshape(N_s, 8), ds, t, s0, dt, N_t)
+        for j in range(0, 257, 16):
+            assert np.array_equal(out[j].T, rf.obtain_reference(x, ds, N_s, t, s0[j], dt, N_t)), j
+    assert mpc.obtain_reference(x.reshape(N_s, 8), ds, t, np.zeros(0), dt, N_t).shape == (0, N_t, 7)
