@@ -23,4 +23,4 @@ for rep in range(4):
     dt_host = time.time() - t
     ms = mpc.last_kernel_ms
     a, d, rf = mpc.counters()
-    print(f"B={B} kernel {ms:.2f} ms  -> {B/ms*1e3:.0f} QP/s ; host call {dt_host*1e3:.1f} ms; exit!=0 {(r.exitflag!=0).sum()} iters mean {r.iters.mean():.1f} max {r.iters.max()} adds/QP {a/B:.1f} drops/QP {d/B:.1f} refresh/QP {rf/B:.2f} slack>0 {(r.slack_opt>0).sum()}")
+    print(f"B={B} last chunk of the pipelined host call: kernel {ms:.2f} ms (see gpu_time_dev.py for device-resident timing); host call {dt_host*1e3:.1f} ms; exit!=0 {(r.exitflag!=0).sum()} iters mean {r.iters.mean():.1f} max {r.iters.max()} adds/QP {a/B:.1f} drops/QP {d/B:.1f} refresh/QP {rf/B:.2f} slack>0 {(r.slack_opt>0).sum()}")
