@@ -66,6 +66,8 @@ struct SmemV2 {
     double Gs[N * D::NU * D::NX];      // G_s = B' W_{s+1}: cost Gramian seen from the controls of step s
     double Wi[N * D::NU * D::NU];      // (Lambda_s)^(-T/2) / sqrt(2): the diagonal blocks of J
     double Lam3[N * 3];                // Lambda_s (a, b, d)
+    static constexpr bool TWOPHASE = C::NR > 8;        // many rows per step: evaluate xs = B_bar_c u first, then the rows
+    double xs[TWOPHASE ? C::NXS * N : 1];              // constraint-state perturbations per step (two-phase search)
     double scal[8];                    // 0 cost const
     alignas(8) fsae_params prm;        // this problem's parameter set (copied once: no global loads in the loops)
     alignas(8) unsigned long long mbar; // mbarrier of the input staging
@@ -115,6 +117,80 @@ struct MpcProb {
         static_assert(NU == 2, "paired (double2) row loads assume two controls per step");
         const int tid = threadIdx.x;
         const double* x = S.gi.x;
+        if constexpr (S_t::TWOPHASE) {
+            // Many rows per step (dynamic model: 17): (a) the NCR x N dot products xs[c][k] = B_bar_c[k] . u
+            // spread over ALL threads -- two lanes for the long ones (k >= K2), one for the short --
+            // then (b) the NROWS + nV slots dealt round-robin.  One extra barrier, balanced work.
+            constexpr int NCR = C::NCR;
+            constexpr int K2 = (2 * N - NT / NCR) > 0 ? (2 * N - NT / NCR) : 0;
+            static_assert(K2 <= N && (2 * (N - K2) + K2) * NCR <= NT, "two-phase search thread map");
+            constexpr int NP2 = (N - K2) * NCR;             // dot products with two lanes
+            static_assert((2 * NP2) % 32 == 0, "the two-lane dot products fill whole warps");
+            int c = -1, k = 0, half = 0, lanes = 1;
+            if (tid < 2 * NP2) { const int p = tid >> 1; half = tid & 1; lanes = 2; c = p / (N - K2); k = K2 + p - c * (N - K2); }
+            else if (K2 > 0 && tid - 2 * NP2 < K2 * NCR) { const int q = tid - 2 * NP2; c = q / K2; k = q - c * K2; }
+            double acc = 0.0, ai[C::NINT > 0 ? C::NINT : 1];
+#pragma unroll
+            for (int ci = 0; ci < C::NINT; ++ci) ai[ci] = 0.0;
+            if (c >= 0) {
+                const int np = k + 1;                         // double2 pairs of this row
+                const int h = (lanes == 2) ? (np + 1) >> 1 : np;
+                const int p0 = half * h, p1 = (p0 + h < np) ? p0 + h : np;
+                const double* brow = S.Bf + S_t::bfc(c) * D::NPK + D::pk(k, 0);
+                double a1 = 0.0;
+#pragma unroll 4
+                for (int pp = p0; pp < p1; ++pp) {
+                    const double2 xx = *reinterpret_cast<const double2*>(&x[2 * pp]);
+                    const double2 bb = *reinterpret_cast<const double2*>(&brow[2 * pp]);
+                    acc = fma(bb.x, xx.x, acc);
+                    a1 = fma(bb.y, xx.y, a1);
+                    if (c == 0) {
+#pragma unroll
+                        for (int ci = 0; ci < C::NINT; ++ci) ai[ci] += (C::int_ucol(ci) == 0) ? xx.x : xx.y;
+                    }
+                }
+                acc += a1;
+            }
+            if (tid < 2 * NP2) {                             // whole warps (2 * NP2 is a multiple of 32 for the supported sizes)
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+#pragma unroll
+                for (int ci = 0; ci < C::NINT; ++ci) ai[ci] += __shfl_xor_sync(0xffffffffu, ai[ci], 1);
+            }
+            if (c >= 0 && half == 0) {
+                S.xs[c * N + k] = acc;
+                if (c == 0) {
+#pragma unroll
+                    for (int ci = 0; ci < C::NINT; ++ci) S.xs[(NCR + ci) * N + k] = ai[ci] * dt;
+                }
+            }
+            __syncthreads();
+            for (int sl_ = tid; sl_ < D::NROWS + nV; sl_ += NT) {
+                if (sl_ < D::NROWS) {
+                    const int r = sl_ / N, kk = sl_ - r * N, slot = nV + sl_;
+                    if (S.gi.status[slot] != 0) continue;
+                    double xsk[C::NXS];
+#pragma unroll
+                    for (int cc = 0; cc < C::NXS; ++cc) xsk[cc] = S.xs[cc * N + kk];
+                    const double rv = C::row_value(r, xsk, S.pc + kk * C::NPC, S.cg, x[NU * kk]);
+                    const int sl = C::row_slack(r);
+                    const double sv = sl >= 0 ? x[nU + sl] : 0.0;
+                    const double vlo = rv + sv - S.rlo[sl_];
+                    const double vup = S.rup[sl_] - rv + sv;
+                    if (vlo < best) { best = vlo; best_i = slot * 2; }
+                    if (vup < best) { best = vup; best_i = slot * 2 + 1; }
+                } else {
+                    const int slot = sl_ - D::NROWS;
+                    if (S.gi.status[slot] != 0) continue;
+                    const double xv = x[slot];
+                    const double lb = (slot < nU) ? P.u_lb[slot % NU] : 0.0;
+                    const double ub = (slot < nU) ? P.u_ub[slot % NU] : INFINITY;
+                    const double vlo = xv - lb, vup = ub - xv;
+                    if (vlo < best) { best = vlo; best_i = slot * 2; }
+                    if (vup < best) { best = vup; best_i = slot * 2 + 1; }
+                }
+            }
+            return;
+        }
         for (int rt = tid; rt < ROWT; rt += NT) {            // warp-uniform trip count
             const int k = rt >> 2, part = rt & 3;
             const bool valid = k < N;

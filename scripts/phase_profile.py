@@ -30,11 +30,16 @@ if os.environ.get("FSAE_N") == "80":          # horizon 80: the committed fsg201
     tr_ = lambda a: np.ascontiguousarray(a.transpose(0, 2, 1)[pick])
     x0, xr, xl, ul = g["x0"][pick].copy(), tr_(g["x_ref"]), tr_(g["x_lin"]), tr_(g["u_lin"])
 out = (C.c_uint64 * 16)()
-mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, 0.05, xl, ul)
+step, kw = mpc.ltvmpc_kinetmatic_curvilinear, {}
+if os.environ.get("FSAE_MODEL") == "dynamic":
+    x0, xr, xl, ul = wl.perturbed_batch("dynamic", "fss2019", B, 0)
+    mpc.set_params(1, fm.default_params(fm.DYNAMIC))
+    step, kw = mpc.ltvmpc_dynamic_curvilinear, dict(track_id=np.ones(B, np.int32), param_id=np.ones(B, np.int32))
+step(x0, xr, 0.05, xl, ul, **kw)
 lib.fsae_profile_read(mpc._ctx, out, 1)
 mpc.counters(reset=True)
 lib.fsae_profile_read_stages(mpc._ctx, sg, 1)
-r = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, 0.05, xl, ul)
+r = step(x0, xr, 0.05, xl, ul, **kw)
 lib.fsae_profile_read(mpc._ctx, out, 1)
 adds, drops, refr = mpc.counters()
 names = ["loop/refresh/end-of-block barrier", "P1 search (policy)", "P1 top-KB argmin+barrier", "P2 normals", "(unused)",
