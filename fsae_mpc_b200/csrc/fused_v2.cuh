@@ -138,7 +138,6 @@ struct MpcProb {
                 const int p0 = half * h, p1 = (p0 + h < np) ? p0 + h : np;
                 const double* brow = S.Bf + S_t::bfc(c) * D::NPK + D::pk(k, 0);
                 double a1 = 0.0;
-#pragma unroll 4
                 for (int pp = p0; pp < p1; ++pp) {
                     const double2 xx = *reinterpret_cast<const double2*>(&x[2 * pp]);
                     const double2 bb = *reinterpret_cast<const double2*>(&brow[2 * pp]);
