@@ -50,7 +50,10 @@ struct SmemV2 {
             alignas(16) double ul[N * D::NU];
             double dd[N * D::NX];
             double Kc[N * D::NU * D::NX];      // Riccati feedback gains K_s (adjoint rows -> J)
-            double wgram[6 * D::NX * D::NX + 3 * D::NU * D::NX];   // recursion scratch: W, P (double-buffered), W A, P A; B'P, S, K
+            union {                             // recursion scratch: W, P (double-buffered), W A, P A; B'P, S, K
+                double wgram[6 * D::NX * D::NX + 3 * D::NU * D::NX];
+                alignas(16) double wgram2[(6 * D::NX + 3 * D::NU) * ((D::NX + 1) & ~1)];   // rows padded to an even length
+            };
         };
         alignas(16) double Msm[GiTile<G>::SM_DOUBLES > 0 ? GiTile<G>::SM_DOUBLES : 2];   // shared part of the operator tiles
     };
@@ -439,6 +442,135 @@ __device__ __forceinline__ void horizon_recursions(S_t& S, const fsae_params& P)
     }
 }
 
+// The same two recursions for small state dimensions (NX^2 <= 32: one matrix entry per lane), tuned for the
+// critical path of the kinematic kernel: rows padded to an even length and read as double2 (W, P are
+// symmetric, so columns are read as rows; W A and P A are stored transposed for the same reason), B and the
+// lane's column of A_s in registers.  ~40 shared-memory loads per stage instead of ~66.
+template <class Model, int N, class S_t>
+__device__ __forceinline__ void horizon_recursions_small(S_t& S, const fsae_params& P) {
+    using D = Dims<Model, N>;
+    using C = Cons<Model>;
+    constexpr int NX = D::NX, NU = D::NU, NR_ = C::NREAL, NXP = (NX + 1) & ~1, NV2 = NXP / 2;
+    static_assert(NX * NX <= 32 && NU == 2, "one matrix entry per lane, 2 x 2 Lambda blocks");
+    const int lane = threadIdx.x & 31;
+    const int e = lane < NX * NX ? lane : 0;
+    const int i = e / NX, j = e - i * NX, c = i < NU ? i : NU - 1;
+    const bool le = lane < NX * NX, lb_ = lane < NU * NX;
+    // scratch (doubles): W [2][NX][NXP], P [2][NX][NXP], (W A)' [NX][NXP], (P A)' [NX][NXP], B'P [NU][NXP], S [NU][NXP], K [NU][NXP]
+    double* Wb = S.wgram2;
+    double* Pb = Wb + 2 * NX * NXP;
+    double* TWt = Pb + 2 * NX * NXP;
+    double* TPt = TWt + NX * NXP;
+    double* BP = TPt + NX * NXP;
+    double* Sm = BP + NU * NXP;
+    double* Kx = Sm + NU * NXP;
+    auto ldrow = [](const double* M, int r, double (&o)[NXP]) {
+        const double2* p2 = reinterpret_cast<const double2*>(M + r * NXP);
+#pragma unroll
+        for (int h = 0; h < NV2; ++h) { const double2 v = p2[h]; o[2 * h] = v.x; o[2 * h + 1] = v.y; }
+    };
+    double bc[NX], bb0[NX], bb1[NX];
+#pragma unroll
+    for (int l = 0; l < NX; ++l) { bc[l] = S.B1[l * NU + c]; bb0[l] = S.B1[l * NU]; bb1[l] = S.B1[l * NU + 1]; }
+    const double r0 = P.R[0], r1 = P.R[1], qd = (i == j) ? P.Q[i] : 0.0;
+    for (int t = lane; t < 2 * NX * NXP; t += 32) {
+        const int rr = (t % (NX * NXP)) / NXP, cc = t % NXP;
+        const double v = (rr == cc) ? P.Q_terminal[rr] : 0.0;
+        Wb[t] = (t < NX * NXP) ? v : 0.0;
+        Pb[t] = (t < NX * NXP) ? v : 0.0;
+    }
+    for (int t = lane; t < 2 * NX * NXP; t += 32) { TWt[t] = 0.0; }      // (W A)', (P A)' incl. padding
+    __syncwarp();
+    int cur = 0;
+    RSTAGE_DECL;
+    for (int st = N - 1; st >= 0; --st) {
+        const double* W = Wb + cur * NX * NXP;
+        const double* Pm = Pb + cur * NX * NXP;
+        const double* As = S.Ad + st * NR_ * NX;
+        double aj[NR_];
+#pragma unroll
+        for (int l = 0; l < NR_; ++l) aj[l] = As[l * NX + j];
+        // phase 1: (W A)[i][j], (P A)[i][j];  (B'P)[c][j], G_s[c][j] = (B'W)[c][j]
+        {
+            double wi[NXP], wj[NXP], pi[NXP], pj[NXP];
+            ldrow(W, i, wi); ldrow(W, j, wj); ldrow(Pm, i, pi); ldrow(Pm, j, pj);
+            double tw = (j >= NR_) ? W[i * NXP + j] : 0.0, tp = (j >= NR_) ? Pm[i * NXP + j] : 0.0, bp = 0.0, wb = 0.0;
+#pragma unroll
+            for (int l = 0; l < NX; ++l) {
+                bp = fma(bc[l], pj[l], bp);
+                wb = fma(bc[l], wj[l], wb);
+                if (l < NR_) { tw = fma(wi[l], aj[l], tw); tp = fma(pi[l], aj[l], tp); }
+            }
+            if (le) { TWt[j * NXP + i] = tw; TPt[j * NXP + i] = tp; }
+            if (lb_) { BP[c * NXP + j] = bp; S.Gs[(st * NU + c) * NX + j] = wb; }
+        }
+        __syncwarp();
+        RSTAGE(0);
+        // phase 2 (lane = (c, j)): S = (B'P) A column j, Lambda = R + (B'P) B, K = -Lambda^-1 S
+        {
+            double b0[NXP], b1[NXP];
+            ldrow(BP, 0, b0); ldrow(BP, 1, b1);
+            double s0 = (j >= NR_) ? BP[j] : 0.0, s1 = (j >= NR_) ? BP[NXP + j] : 0.0;
+            double la = r0, lb = 0.0, ld = r1;
+#pragma unroll
+            for (int l = 0; l < NX; ++l) {
+                la = fma(b0[l], bb0[l], la);
+                lb = fma(b0[l], bb1[l], lb);
+                ld = fma(b1[l], bb1[l], ld);
+                if (l < NR_) { s0 = fma(b0[l], aj[l], s0); s1 = fma(b1[l], aj[l], s1); }
+            }
+            const double rdet = __drcp_rn(fma(la, ld, -lb * lb));
+            const double kv = (c == 0) ? (lb * s1 - ld * s0) * rdet : (lb * s0 - la * s1) * rdet;
+            if (lb_) {
+                Sm[c * NXP + j] = (c == 0) ? s0 : s1;
+                Kx[c * NXP + j] = kv;
+                S.Kc[(st * NU + c) * NX + j] = kv;
+            }
+            if (lane < 3) S.Lam3[st * 3 + lane] = (lane == 0) ? la : (lane == 1 ? lb : ld);
+        }
+        __syncwarp();
+        if (lane == 0) {                           // K_st and G_st are in shared memory: publish the stage
+            __threadfence_block();
+            *(volatile int*)&S.prog = st;
+        }
+        RSTAGE(1);
+        if (st == 0) break;
+        // phase 3: W'[i][j] = Q + (A'(W A))[i][j],  P'[i][j] = Q + (A'(P A))[i][j] + (S'K)[i][j]
+        {
+            double tw[NXP], tp[NXP];
+            ldrow(TWt, j, tw); ldrow(TPt, j, tp);
+            double aw = qd + ((i >= NR_) ? TWt[j * NXP + i] : 0.0);
+            double ap = qd + ((i >= NR_) ? TPt[j * NXP + i] : 0.0);
+#pragma unroll
+            for (int l = 0; l < NR_; ++l) {
+                const double al = As[l * NX + i];
+                aw = fma(al, tw[l], aw);
+                ap = fma(al, tp[l], ap);
+            }
+            double sk = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < NU; ++cc) sk = fma(Sm[cc * NXP + i], Kx[cc * NXP + j], sk);
+            if (le) {
+                Wb[(cur ^ 1) * NX * NXP + i * NXP + j] = aw;
+                Pb[(cur ^ 1) * NX * NXP + i * NXP + j] = ap + sk;
+            }
+        }
+        __syncwarp();
+        RSTAGE(2);
+        cur ^= 1;
+    }
+    for (int st = lane; st < N; st += 32) {
+        const double la = S.Lam3[st * 3], lb = S.Lam3[st * 3 + 1], ld = S.Lam3[st * 3 + 2];
+        const double i11 = rsqrt(la), l21 = lb * i11;
+        const double i22 = rsqrt(fma(-l21, l21, ld));
+        const double r2 = 0.70710678118654752440;
+        S.Wi[st * 4 + 0] = r2 * i11;
+        S.Wi[st * 4 + 1] = -r2 * l21 * i11 * i22;
+        S.Wi[st * 4 + 2] = 0.0;
+        S.Wi[st * 4 + 3] = r2 * i22;
+    }
+}
+
 template <class Model, int N, int MINB, int NW_ = 8, int KB_ = 1, int CSR_ = -1>
 __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchArgs a) {
     using D = Dims<Model, N>;
@@ -550,7 +682,10 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
         if (OVL) asm volatile("bar.sync 1, %0;" ::"r"(WNT) : "memory");
         else __syncthreads();
     };
-    if (warp == GW) horizon_recursions<true, true, Model, N>(S, P);
+    if (warp == GW) {
+        if constexpr (NX * NX <= 32) horizon_recursions_small<Model, N>(S, P);
+        else horizon_recursions<true, true, Model, N>(S, P);
+    }
     if (warp == NW - 1) {
         if (lane == 0) {
             double xp[NX], xn[NX];
