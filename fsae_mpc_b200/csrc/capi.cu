@@ -436,6 +436,9 @@ static int launch_fused_long(fsae_ctx* ctx, BatchArgs a, cudaStream_t st) {
 template <class Model, int N, int MINB, int NW = 8, int KB = 1, int CSR = -1>
 static int launch_fused_v2(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
     using S_t = SmemV2<Model, N, NW, KB, CSR>;
+    // the occupancy the kernel was tuned for must survive every change of the shared-memory layout:
+    // 228 KB per SM, 1 KB reserved per resident CTA
+    static_assert((size_t)MINB * (sizeof(S_t) + 1024) <= 233472, "MINB CTAs per SM no longer fit shared memory");
     auto kern = ltvmpc_fused_v2_kernel<Model, N, MINB, NW, KB, CSR>;
     static bool configured[64] = {false};
     if (!configured[ctx->device & 63]) {
