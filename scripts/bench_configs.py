@@ -89,6 +89,18 @@ t0 = time.perf_counter(); rs = mpc.ltvmpc_sqp(fm.KINEMATIC, x0, xr, DT, xl, ul, 
 out.append({"config": "configs[3] SQP: repeated relinearise+QP, batch 16,384, fso2020", "n_sqp": n_sqp, "batch_per_gpu": B,
             "e2e_host_api_qp_per_s": B * n_sqp / (t1 - t0), "e2e_host_api_ms": (t1 - t0) * 1e3, "launches": mpc.launch_count - l0,
             "exitflag_nonzero": int((rs.exitflag != 0).sum())})
+# configs[0] scaled out: main.m's closed loop (projection, reference, fused MPC step, actuator PIDs, plant) for B vehicles
+Bv, n_sim = (1024, 20) if quick else (16384, 100)
+rng = np.random.default_rng(7 + rank)
+plant0 = np.zeros((Bv, 7))
+plant0[:, 1] = rng.uniform(-0.3, 0.3, Bv)           # lateral offset from the centre line at the start
+plant0[:, 2] = rng.uniform(-0.05, 0.05, Bv)
+mpc.closed_loop(fm.KINEMATIC, plant0[:64], 5, history=False)
+l0 = mpc.launch_count
+t0 = time.perf_counter(); cl = mpc.closed_loop(fm.KINEMATIC, plant0, n_sim, history=False); t1 = time.perf_counter()
+out.append({"config": "configs[0] as a batch: main.m closed loop on fsg2019 for B vehicles (kinematic LTV-MPC in the loop)",
+            "vehicles": Bv, "sim_steps": n_sim, "wall_ms": (t1 - t0) * 1e3, "mpc_steps_per_s": Bv * n_sim / (t1 - t0),
+            "launches": mpc.launch_count - l0, "steps_done_min": int(cl["steps"].min())})
 # configs[4]
 sweep = []
 for N in (20, 40, 80):
