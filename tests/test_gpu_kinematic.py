@@ -271,3 +271,30 @@ def test_fused_kernel_taps_hessian_gradient_and_operator(mpc, model_name, N):
         # slack columns lead: unit vectors on the slack rows, nothing else
         assert np.array_equal(M[b][:, :NS], np.eye(nV)[:, nU:])
         assert np.abs(M[b][nU:, NS:]).max() == 0.0
+
+
+@pytest.mark.parametrize("model_name,N,B", [("kinematic", 40, 3000), ("kinematic", 20, 3000), ("kinematic", 80, 300), ("dynamic", 40, 1500)])
+def test_results_are_deterministic(mpc, model_name, N, B):
+    """The kernels synchronise warps through named barriers, double-buffered partial sums and a published stage
+    flag; a missing fence or barrier would show up as run-to-run differences.  Same inputs, three runs (the batch
+    is larger than the number of CTA slots, so block scheduling differs between runs): bit-identical outputs."""
+    import fsae_mpc_b200 as fm
+    from fsae_mpc_b200 import workload as wl
+    if N == 80:
+        g = load_golden("kinematic_lap_fsg2019_N80.npz")
+        pick = np.arange(B) % g["x0"].shape[0]
+        x0, xr, xl, ul = g["x0"][pick], c_layout(g["x_ref"])[pick], c_layout(g["x_lin"])[pick], c_layout(g["u_lin"])[pick]
+        x0 = x0 + np.random.default_rng(1).uniform(-0.05, 0.05, x0.shape) * np.array([0, 1, 0.2, 1, 0.2])
+    else:
+        x0, xr, xl, ul = wl.perturbed_batch(model_name, "fsg2019" if model_name == "kinematic" else "fss2019", B, seed=21)
+        xr, xl, ul = (np.ascontiguousarray(a[:, :N]) for a in (xr, xl, ul))
+    kw = {}
+    step = mpc.ltvmpc_kinetmatic_curvilinear
+    if model_name == "dynamic":
+        mpc.set_params(3, fm.default_params(fm.DYNAMIC))
+        kw = dict(track_id=np.ones(B, np.int32), param_id=np.full(B, 3, np.int32))
+        step = mpc.ltvmpc_dynamic_curvilinear
+    runs = [step(x0, xr, DT, xl, ul, **kw) for _ in range(3)]
+    for r in runs[1:]:
+        for k in ("u_opt", "x_opt", "fval", "slack_opt", "exitflag", "iters", "workingSetB", "workingSetC"):
+            assert np.array_equal(getattr(r, k), getattr(runs[0], k)), k
