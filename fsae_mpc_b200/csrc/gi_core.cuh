@@ -629,7 +629,7 @@ struct GiOps {
                     sp = cviol[0] + dsum;
                     if (!(sp < -tol)) { more = false; PHASE_COUNT(15); }
                 }
-                double d2 = 0.0, t1 = INFINITY, inv_d2 = 0.0, t = 0.0;
+                double d2 = 0.0, t1 = INFINITY, inv_d2 = 0.0, t = 0.0, sgd = 0.0, beta = 0.0;
                 int l = -1;
                 bool full = false, primal = false;
                 if (more) {
@@ -655,6 +655,19 @@ struct GiOps {
                     }
                     const bool lin_dep = !(d2 > 1e-13 * fmax(1.0, nn));
                     inv_d2 = __drcp_rn(d2);
+                    {
+                        // Householder scalars of a possible add (rsqrt + reciprocal: ~150 cycles of dependent latency),
+                        // issued here so that they overlap the primal step instead of delaying the tile update
+                        const int qs = q >> 5, ql = q & 31;
+                        double yq_l = 0.0;
+#pragma unroll
+                        for (int s = 0; s < CS; ++s)
+                            if (s == qs) yq_l = y[s];
+                        const double yqv = __shfl_sync(0xffffffffu, yq_l, ql);
+                        const double delta = d2 * rsqrt(d2);
+                        sgd = (yqv >= 0.0) ? delta : -delta;
+                        beta = __drcp_rn(d2 + fabs(yqv) * delta);
+                    }
                     const double t2 = lin_dep ? INFINITY : (sp < 0.0 ? -sp * inv_d2 : 0.0);
                     full = (t2 <= t1);
                     if (piggy && !full) { --st.iters; PHASE_COUNT(14); break; }     // left to the next search
@@ -698,14 +711,6 @@ struct GiOps {
                                 }
                         }
                         __syncwarp();
-                        const double delta = d2 * rsqrt(d2);
-                        double yq_l = 0.0;
-#pragma unroll
-                        for (int s = 0; s < CS; ++s)
-                            if (s == qs) yq_l = y[s];
-                        const double yqv = __shfl_sync(0xffffffffu, yq_l, ql);
-                        const double sgd = (yqv >= 0.0) ? delta : -delta;
-                        const double beta = __drcp_rn(d2 + fabs(yqv) * delta);
                         // Column slots entirely left of q take  m - kr y,  slots entirely right of it
                         // m - wr y  (one FMA per element, warp-uniform choice); only the slot that holds
                         // column q mixes the three cases:  c*m - kr*ya - wr*yb  with (c, ya, yb) =
