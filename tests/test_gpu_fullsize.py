@@ -20,17 +20,35 @@ pytestmark = pytest.mark.gpu
 INF = 1e19
 
 
-def _certify(mpc, model, track, B, chunk, tid, pid, max_infeasible):
+def _certify(mpc, model, track, B, chunk, tid, pid, max_infeasible, N=40):
     import fsae_mpc_b200 as fm
     from fsae_mpc_b200 import workload as wl
     mid = fm.KINEMATIC if model == "kinematic" else fm.DYNAMIC
-    x0, xr, xl, ul = wl.perturbed_batch(model, track, B, seed=1000)          # bench.py's rank-0 batch
+    if N == 80:                                                              # the committed fsg2019 lap, perturbed
+        from conftest import load_golden, c_layout
+        g = load_golden("kinematic_lap_fsg2019_N80.npz")
+        rng = np.random.default_rng(1000)
+        pick = rng.integers(g["x0"].shape[0], size=B)
+        x0 = g["x0"][pick].copy()
+        x0[:, 1] += rng.uniform(-0.3, 0.3, B); x0[:, 2] += rng.uniform(-0.08, 0.08, B)
+        x0[:, 3] = np.maximum(0.5, x0[:, 3] + rng.uniform(-1.5, 1.5, B)); x0[:, -1] += rng.uniform(-0.05, 0.05, B)
+        xr, xl, ul = c_layout(g["x_ref"])[pick], c_layout(g["x_lin"])[pick], c_layout(g["u_lin"])[pick]
+    else:
+        x0, xr, xl, ul = wl.perturbed_batch(model, track, B, seed=1000)      # bench.py's rank-0 batch
+        xr, xl, ul = (np.ascontiguousarray(a[:, :N]) for a in (xr, xl, ul))  # N = 20: the first 20 steps
     step = mpc.ltvmpc_kinetmatic_curvilinear if model == "kinematic" else mpc.ltvmpc_dynamic_curvilinear
     t_id, p_id = np.full(B, tid, np.int32), np.full(B, pid, np.int32)
     r = step(x0, xr, DT, xl, ul, track_id=t_id, param_id=p_id)
     ok = r.exitflag == 0
     assert set(np.unique(r.exitflag)) <= {0, -2}
     assert (~ok).sum() <= max_infeasible, f"{(~ok).sum()} problems not solved"
+    if model == "kinematic":
+        # An infeasibility verdict must be one: the steering angle is a pure integrator with a hard bound,
+        # delta_1 = delta_0 + dt * u_2, |u_2| <= 0.4, |delta_1| <= 0.4, so the problem is infeasible exactly when
+        # the (perturbed) start value lies more than dt * 0.4 outside the bound.
+        excess = np.abs(x0[:, 4]) - (0.4 + 0.4 * DT)
+        clear = np.abs(excess) > 1e-7
+        assert np.array_equal((~ok)[clear], (excess > 0)[clear]), "exitflag -2 does not coincide with infeasible steering"
     worst = dict(primal=0.0, active=0.0, stat=0.0, dual=0.0)
     for lo in range(0, B, chunk):
         sl = slice(lo, min(B, lo + chunk))
@@ -87,5 +105,16 @@ def test_full_dynamic_batch_is_kkt_certified(mpc):
     mpc.set_params(3, fm.default_params(fm.DYNAMIC))
     worst, ninf = _certify(mpc, "dynamic", "fss2019", 32768, 1024, 1, 3, max_infeasible=0)
     print("dynamic 32,768: worst scaled KKT residuals", worst)
+    assert worst["primal"] <= 1e-7 and worst["active"] <= 1e-7, worst
+    assert worst["stat"] <= 1e-7 and worst["dual"] <= 1e-6, worst
+
+
+@pytest.mark.parametrize("N,track,tid,B,chunk", [(20, "fso2020", 2, 16384, 8192), (80, "fsg2019", 0, 2048, 512), (40, "fss2019", 1, 8192, 4096)])
+def test_sweep_batches_are_kkt_certified(mpc, N, track, tid, B, chunk):
+    """configs[4]: other horizons and tracks (horizon 80 runs the split register/shared-memory tile).  Perturbed
+    start states can make a problem infeasible (steering beyond its hard bound at step 0): those are reported as
+    exitflag -2, everything else must be a KKT point."""
+    worst, ninf = _certify(mpc, "kinematic", track, B, chunk, tid, 0, max_infeasible=B // 20, N=N)
+    print(f"kinematic N={N} {track} {B}: infeasible {ninf}, worst scaled KKT residuals", worst)
     assert worst["primal"] <= 1e-7 and worst["active"] <= 1e-7, worst
     assert worst["stat"] <= 1e-7 and worst["dual"] <= 1e-6, worst
