@@ -1,18 +1,20 @@
 // Fused per-problem LTV-MPC step, version 2 (the product kernel).
 //
-// One CTA (8 warps) per problem.  The nV x nV dual active-set operator M = [K1 | J2] never
-// touches shared memory: it lives in REGISTERS, tiled so that
-//     warp w  owns rows    w*RPW .. w*RPW+RPW-1           (RPW = ceil(nV/8)  = 11 for nV = 81)
+// One CTA per problem (kinematic N = 40: 6 warps, 2 CTAs/SM; N = 20: 4 warps x 5; N = 80: 12 warps with
+// the operator tile split between registers and shared memory; dynamic: 8 warps).  The nV x nV dual
+// active-set operator M = [K1 | J2] lives in REGISTERS, tiled so that
+//     warp w  owns rows    w*RPW .. w*RPW+RPW-1           (RPW = ceil(nV/NW) = 14 for nV = 81, 6 warps)
 //     lane l  owns columns l, l+32, l+64                   (CS  = ceil(nV/32) = 3)
-// i.e. every thread holds an RPW x CS tile (33 doubles).  With that layout
-//   * y = M'n     : 33 FMAs per thread + ONE cross-warp sum through shared memory,
-//   * z = J2 y2   : 33 FMAs per thread + an in-warp reduce-scatter (shuffles only),
-//   * rank-1 update of M : 33 FMAs per thread, no communication,
+// i.e. every thread holds an RPW x CS tile (42 doubles).  With that layout
+//   * y = M'n     : 42 FMAs per thread + ONE cross-warp sum through shared memory,
+//   * z = J2 y2   : 42 FMAs per thread + an in-warp reduce-scatter (shuffles only),
+//   * rank-1 update of M : one FMA per element, no communication,
 // and every warp derives step lengths / add-or-drop decisions redundantly from the same
-// data, so an iteration needs 4 block barriers and no serial "warp 0 decides" section.
-// The condensed Hessian is accumulated, factorised (LDL' by symmetric elimination) and
-// inverted in the same register tiles, so the factor goes H -> J = L^-T without leaving
-// the register file.
+// data, so an add iteration needs 3 block barriers and no serial "warp 0 decides" section.
+// Setup without a dense factorisation: a Gramian and a Riccati recursion over the horizon (one
+// warp, horizon_recursions*) give every entry of the condensed Hessian as one short dot product
+// and J (J'HJ = I) as the closed-loop response to unit innovations, its rows produced by adjoint
+// threads that follow the recursion stage by stage.
 //
 // Pipeline and reference mapping: see fused_v1.cuh header (same stages).
 #pragma once

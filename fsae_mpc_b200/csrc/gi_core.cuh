@@ -6,14 +6,21 @@
 // Goldfarb-Idnani (Math. Prog. 27, 1983) in operator form: the nV x nV matrix M = [K1 | J2]
 //   J2 : H-orthonormal basis of the null space of the working set      (J2' H J2 = I, N' J2 = 0)
 //   K1 : multiplier operator H^-1 N (N' H^-1 N)^-1                       (N' K1 = I, J2' H K1 = 0)
-// lives in REGISTERS: warp w owns rows w*RPW .. w*RPW+RPW-1, lane l owns columns l, l+32, ...
-// (an RPW x CS tile per thread).  One iteration:
-//   y = M'n (one cross-warp sum through smem), step lengths and the add/drop decision computed
-//   redundantly by every warp, z = J2 y2 (in-warp reduce-scatter), then either
-//   add : Householder on J2 + rank-1 on K1 (3 FP64 ops per element, no communication), or
+// lives in REGISTERS (GiTile; long horizons keep some column slots in shared memory): warp w owns rows
+// w*RPW .. w*RPW+RPW-1, lane l owns columns l, l+32, ... (an RPW x CS tile per thread).  One iteration:
+//   exact arg-min of the violations with two 32-bit REDUX per warp on an order-preserving key,
+//   y = M'n (one cross-warp sum through smem; a variable bound publishes a row of M instead),
+//   z = J2 y2 (in-warp reduce-scatter), step lengths and the add/drop decision computed redundantly
+//   by every warp, then either
+//   add : Householder on J2 + rank-1 on K1 (one FMA per element outside the column slot of q), or
 //   drop: K1 += k r'^T with r' = -K1' H k / k'Hk, column swap by shuffle.
-// The problem-specific parts (how slots are evaluated and what their normals are) come from a
-// policy object:  search(best, best_i),  normal_entry(slot, side, i),  norm2(slot).
+// Termination: a refresh (Newton step on the active manifold, multipliers from stationarity) after
+// every run of partial steps; columns whose recomputed multiplier is negative are dropped.
+// Template knobs (GiCfg): warps per problem NW, constraints taken per search KB (block adds),
+// column slots in registers CSR.
+// The problem-specific parts (how slots are evaluated and what their normals are) come from a policy
+// object:  search(best, best_i),  normal_prepare(slot, side) + normal_entry(prep, i),  norm2(slot),
+// is_unit(slot).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
