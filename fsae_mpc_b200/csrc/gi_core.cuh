@@ -118,6 +118,7 @@ struct GiCfg {
     static constexpr int CS = (NVMAX + 32) / 32;             // column slots per lane (one spare column)
     static constexpr int CP = CS * 32;                       // padded columns
     static constexpr int SP = (NVMAX > 96) ? 8 : 3;          // partial sums per row of a packed symv (long horizons: H in L2)
+    static constexpr bool TWO_LEVEL_SUM = NW_ >= 10;         // cross-warp sum of M'v: slice per warp + second barrier
     static constexpr int CSR = (CSR_ < 0 || CSR_ > CS) ? CS : CSR_;   // column slots held in registers ...
     static constexpr int CSS = CS - CSR;                     // ... and in shared memory (long horizons)
     static constexpr int RH = (RPW <= 8) ? 8 : (RPW <= 16 ? 16 : 32);   // reduce-scatter width
@@ -164,6 +165,7 @@ struct GiSm {
     double rowv[G::RP];                // per-warp row vector scratch (gradient / H k)
     double nvec[G::KB][G::RP];         // per-warp rows of the normals of the block's constraints
     double zrow[G::RP];                // per-warp reduced z
+    double ysum[G::TWO_LEVEL_SUM ? G::CP : 1];   // published cross-warp sums of M'v (two-level variant)
     double xs0[G::RP];                 // x as the block's search saw it (own rows per warp)
     double wpart[G::SP][G::RP];        // symv partials
     double dvec[G::RP];                // LDL' pivots
@@ -203,12 +205,29 @@ struct GiOps {
 #pragma unroll
         for (int s = 0; s < CS; ++s) S.ypart[ybuf][warp][lane + 32 * s] = yp[s];
         __syncthreads();
+        if constexpr (G::TWO_LEVEL_SUM) {
+            // many warps (long horizons): every warp sums a slice of the columns once and publishes it,
+            // instead of every warp summing every column (NW * CS loads per thread)
+            constexpr int CPW = (G::CP + NW - 1) / NW;
+            static_assert(CPW <= 32, "one lane per column of the slice");
+            const int col = warp * CPW + lane;
+            if (lane < CPW && col < G::CP) {
+                double acc = 0.0;
 #pragma unroll
-        for (int s = 0; s < CS; ++s) {
-            double acc = 0.0;
+                for (int w = 0; w < NW; ++w) acc += S.ypart[ybuf][w][col];
+                S.ysum[col] = acc;
+            }
+            __syncthreads();
 #pragma unroll
-            for (int w = 0; w < NW; ++w) acc += S.ypart[ybuf][w][lane + 32 * s];
-            y[s] = acc;
+            for (int s = 0; s < CS; ++s) y[s] = S.ysum[lane + 32 * s];
+        } else {
+#pragma unroll
+            for (int s = 0; s < CS; ++s) {
+                double acc = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) acc += S.ypart[ybuf][w][lane + 32 * s];
+                y[s] = acc;
+            }
         }
         ybuf ^= 1;
         extra_sum = __shfl_sync(0xffffffffu, y[CS - 1], 31);
