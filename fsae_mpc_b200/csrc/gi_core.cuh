@@ -118,7 +118,7 @@ struct GiCfg {
     static constexpr int CS = (NVMAX + 32) / 32;             // column slots per lane (one spare column)
     static constexpr int CP = CS * 32;                       // padded columns
     static constexpr int SP = (NVMAX > 96) ? 8 : 3;          // partial sums per row of a packed symv (long horizons: H in L2)
-    static constexpr bool TWO_LEVEL_SUM = NW_ >= 10;         // cross-warp sum of M'v: slice per warp + second barrier
+    static constexpr bool TWO_LEVEL_SUM = NW_ >= 6;          // cross-warp sum of M'v: slice per warp + second barrier
     static constexpr int CSR = (CSR_ < 0 || CSR_ > CS) ? CS : CSR_;   // column slots held in registers ...
     static constexpr int CSS = CS - CSR;                     // ... and in shared memory (long horizons)
     static constexpr int RH = (RPW <= 8) ? 8 : (RPW <= 16 ? 16 : 32);   // reduce-scatter width
