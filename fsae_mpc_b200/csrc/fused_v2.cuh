@@ -973,9 +973,10 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     {
         static_assert(C::real_state(0) == 0 && C::real_state(C::NREAL - 1) == C::NREAL - 1, "real states come first");
         double* gH = a.dbg_H ? a.dbg_H + (size_t)b * nV * nV : nullptr;
-        for (int e = tid; e < nV * nV; e += NT) {
-            const int i = e / nV, j = e - i * nV;
-            if (j > i) continue;
+        // one warp per row i (rows dealt from the longest down, so the warps finish together), lanes over
+        // the columns j <= i: row quantities are warp-uniform, packed loads and stores are contiguous
+        for (int ir = warp; ir < nV; ir += NW)
+        for (int i = nV - 1 - ir, j = lane; j <= i; j += 32) {
             double h = 0.0;
             if (i < nU) {
                 const int si = i / NU, ci = i - si * NU, cj = j % NU;
