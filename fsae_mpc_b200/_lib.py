@@ -72,6 +72,8 @@ SIGNATURES = {
                                              C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     "fsae_debug_set_taps": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fsae_probe_fp64_tflops": (C.c_int, [_ctx, C.POINTER(C.c_double)]),
+    "fsae_set_host_staging": (C.c_int, [_ctx, C.c_int]),
+    "fsae_last_host_path": (C.c_int, [_ctx]),
 }
 
 _lib = None

@@ -3,8 +3,14 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/fsae_mpc_b200.h"
@@ -37,6 +43,87 @@ struct DevBuf {
     }
 };
 
+// Pinned (page-locked) host buffer, grow-only.
+struct PinBuf {
+    char* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc((void**)&p, bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// Helper threads that move data between the caller's PAGEABLE buffers and the pinned staging ring
+// (MATLAB's mxArrays and plain numpy arrays are pageable: a cudaMemcpyAsync on them is staged by the
+// driver on the calling thread and serialises with everything else).  A job is one memcpy, optionally
+// after a CUDA event (the D2H copy of a chunk into the ring); a latch counts a group of jobs down.
+struct Latch {
+    std::mutex mu;
+    std::condition_variable cv;
+    int n = 0;
+    void reset(int k) { std::lock_guard<std::mutex> l(mu); n = k; }
+    void count_down() { std::lock_guard<std::mutex> l(mu); if (--n <= 0) cv.notify_all(); }
+    void wait() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return n <= 0; }); }
+};
+struct CopyJob {
+    char* dst = nullptr;
+    const char* src = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t after = nullptr;
+    Latch* done = nullptr;
+};
+struct CopyPool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<CopyJob> q;
+    bool stop = false;
+    int device = 0;
+    void start(int n, int dev) {
+        device = dev;
+        for (int i = 0; i < n; ++i) th.emplace_back([this] { run(); });
+    }
+    void run() {
+        cudaSetDevice(device);
+        for (;;) {
+            CopyJob j;
+            {
+                std::unique_lock<std::mutex> l(mu);
+                cv.wait(l, [&] { return stop || !q.empty(); });
+                if (q.empty()) return;
+                j = q.front();
+                q.pop_front();
+            }
+            if (j.after) cudaEventSynchronize(j.after);
+            if (j.bytes) memcpy(j.dst, j.src, j.bytes);
+            if (j.done) j.done->count_down();
+        }
+    }
+    void post(const CopyJob& j) {
+        { std::lock_guard<std::mutex> l(mu); q.push_back(j); }
+        cv.notify_one();
+    }
+    void shutdown() {
+        { std::lock_guard<std::mutex> l(mu); stop = true; }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+        th.clear();
+    }
+    ~CopyPool() { shutdown(); }
+};
+
+constexpr int FSAE_RING = 4;        // slots of the pinned staging ring
+
 struct fsae_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
@@ -56,7 +143,15 @@ struct fsae_ctx {
     unsigned long long* d_counters = nullptr;
     // staging for *_host calls
     DevBuf in[8], out[12];
-    DevBuf m_scratch[2];       // operator slabs of the long-horizon (global-operator) kernel, per stream
+    struct Slab { cudaStream_t st; DevBuf buf; };
+    std::vector<Slab> slabs;   // per-problem L2 slabs of the long-horizon kernels, one pool PER STREAM
+    // pageable callers: pinned staging ring + copy threads (created on first use)
+    PinBuf ring_in[FSAE_RING], ring_out[FSAE_RING];
+    cudaEvent_t ev_ring[FSAE_RING] = {nullptr, nullptr, nullptr, nullptr};
+    CopyPool* copy_pool = nullptr;
+    int copy_threads = 0;
+    int staging_mode = 0;      // 0 auto (stage when a caller buffer is pageable), 1 never, 2 always
+    int last_host_path = 0;    // 0 direct copies, 1 pinned staging ring (fsae_debug_last_host_path)
 };
 
 #define CK(call)                                                                       \
@@ -97,6 +192,33 @@ extern "C" void fsae_default_params(int model, fsae_params* p) {
     p->flat_eps = 1e-8;
 }
 
+// Frees everything a context owns (also on the failure paths of fsae_create).
+static void release_ctx(fsae_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    if (ctx->copy_pool) { delete ctx->copy_pool; ctx->copy_pool = nullptr; }
+    for (auto& b : ctx->in) b.release();
+    for (auto& b : ctx->out) b.release();
+    for (auto& sl : ctx->slabs) sl.buf.release();
+    ctx->slabs.clear();
+    for (auto& b : ctx->ring_in) b.release();
+    for (auto& b : ctx->ring_out) b.release();
+    for (auto& e : ctx->ev_ring) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (int i = 0; i < FSAE_MAX_TRACKS; ++i)
+        if (ctx->d_coef[i]) { cudaFree(ctx->d_coef[i]); ctx->d_coef[i] = nullptr; }
+    if (ctx->d_params) cudaFree(ctx->d_params);
+    if (ctx->d_tracks) cudaFree(ctx->d_tracks);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
 extern "C" int fsae_create(fsae_ctx** out, int device) {
     if (!out) return FSAE_ERR_ARG;
     *out = nullptr;
@@ -111,7 +233,7 @@ extern "C" int fsae_create(fsae_ctx** out, int device) {
     memset(ctx->d_coef, 0, sizeof(ctx->d_coef));
     auto fail = [&](const char* what) {
         fprintf(stderr, "fsae_create: %s failed: %s\n", what, cudaGetErrorString(cudaGetLastError()));
-        delete ctx;
+        release_ctx(ctx);                            // streams, events and buffers made so far
         return FSAE_ERR_CUDA;
     };
     if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice");
@@ -120,6 +242,8 @@ extern "C" int fsae_create(fsae_ctx** out, int device) {
     if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) return fail("event");
     if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail("event2");
+    for (auto& e : ctx->ev_ring)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail("ring events");
     if (cudaMalloc(&ctx->d_params, sizeof(fsae_params) * FSAE_MAX_PARAM_SETS) != cudaSuccess) return fail("malloc params");
     if (cudaMalloc(&ctx->d_tracks, sizeof(DevTrack) * FSAE_MAX_TRACKS) != cudaSuccess) return fail("malloc tracks");
     if (cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) return fail("malloc counters");
@@ -128,30 +252,20 @@ extern "C" int fsae_create(fsae_ctx** out, int device) {
     for (int i = 0; i < FSAE_MAX_PARAM_SETS; ++i) fsae_default_params(FSAE_MODEL_KINEMATIC, &ctx->h_params[i]);
     if (cudaMemcpy(ctx->d_params, ctx->h_params, sizeof(ctx->h_params), cudaMemcpyHostToDevice) != cudaSuccess)
         return fail("memcpy params");
+    {
+        // copy threads of the pageable-host path: FSAE_COPY_THREADS, default min(4, cores / 2)
+        const char* e = getenv("FSAE_COPY_THREADS");
+        int t = e ? atoi(e) : 0;
+        if (t <= 0) { t = (int)std::thread::hardware_concurrency() / 2; if (t > 4) t = 4; }
+        ctx->copy_threads = t < 1 ? 1 : (t > 16 ? 16 : t);
+    }
     *out = ctx;
     return FSAE_OK;
 }
 
 extern "C" int fsae_destroy(fsae_ctx* ctx) {
     if (!ctx) return FSAE_ERR_ARG;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    for (auto& b : ctx->in) b.release();
-    for (auto& b : ctx->out) b.release();
-    for (auto& b : ctx->m_scratch) b.release();
-    for (int i = 0; i < FSAE_MAX_TRACKS; ++i)
-        if (ctx->d_coef[i]) cudaFree(ctx->d_coef[i]);
-    cudaFree(ctx->d_params);
-    cudaFree(ctx->d_tracks);
-    cudaFree(ctx->d_counters);
-    cudaStreamSynchronize(ctx->stream2);
-    cudaStreamDestroy(ctx->stream2);
-    cudaEventDestroy(ctx->ev_fork);
-    cudaEventDestroy(ctx->ev_join);
-    cudaEventDestroy(ctx->ev0);
-    cudaEventDestroy(ctx->ev1);
-    cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    release_ctx(ctx);
     return FSAE_OK;
 }
 
@@ -378,6 +492,16 @@ extern "C" int fsae_condense_host(fsae_ctx* ctx, int model, int B, int N, double
 }
 
 // ------------------------------------------------------------------ fused step
+// Slab pool of the long-horizon kernels, one per stream that ever launched them: concurrent _dev calls on
+// different streams never share per-CTA slabs.  Growing a pool (cudaFree + cudaMalloc) synchronises the
+// device; it happens on the first call of a stream and when a larger batch slice arrives.
+static DevBuf& slab_pool(fsae_ctx* ctx, cudaStream_t st) {
+    for (auto& sl : ctx->slabs)
+        if (sl.st == st) return sl.buf;
+    ctx->slabs.push_back({st, DevBuf()});
+    return ctx->slabs.back().buf;
+}
+
 template <class Model, int N, int NT>
 static int launch_fused_v1(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
     using S_t = SmemV1<Model, N, NT>;
@@ -407,7 +531,7 @@ static int launch_fused_long(fsae_ctx* ctx, BatchArgs a, cudaStream_t st) {
         configured[ctx->device & 63] = true;
     }
     constexpr int SLICE = 2048;
-    DevBuf& pool = ctx->m_scratch[st == ctx->stream2 ? 1 : 0];
+    DevBuf& pool = slab_pool(ctx, st);
     const int nsl = a.B < SLICE ? a.B : SLICE;
     CK(pool.reserve((size_t)nsl * D::nV * D::LD * sizeof(double)));
     const int B = a.B;
@@ -459,7 +583,7 @@ template <class Model, int N, int NW, int CSR>
 static int launch_fused_v2_long(fsae_ctx* ctx, BatchArgs a, cudaStream_t st) {
     using S_t = SmemV2<Model, N, NW, 1, CSR>;
     constexpr int SLICE = 2048;
-    DevBuf& pool = ctx->m_scratch[st == ctx->stream2 ? 1 : 0];
+    DevBuf& pool = slab_pool(ctx, st);
     const int nsl = a.B < SLICE ? a.B : SLICE;
     CK(pool.reserve((size_t)nsl * S_t::SLAB * sizeof(double)));
     const int B = a.B;
@@ -496,6 +620,8 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
         !u_opt || !x_opt || !exitflag || !fval || !slack_opt)
         return FSAE_ERR_ARG;
     if (B == 0) return FSAE_OK;
+    // per-problem ids live on the device and cannot be checked here; the default track can
+    if (!track_id && !ctx->h_tracks[0].coef) { ctx->err = "track 0 not set (fsae_set_track)"; return FSAE_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     BatchArgs a;
@@ -537,6 +663,14 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
     return FSAE_OK;
 }
 
+// true if a caller buffer is ordinary pageable memory (not cudaHostAlloc'ed / cudaHostRegister'ed)
+static bool is_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
 extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double dt,
                                 const int32_t* track_id, const int32_t* param_id,
                                 const double* x0, const double* x_ref,
@@ -554,9 +688,10 @@ extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double d
     CK(cudaSetDevice(ctx->device));
     const int nU = NU * N, nV = nU + NS, nXN = NX * N;
     const int nC = (model == FSAE_MODEL_KINEMATIC) ? 6 * N : 20 * N;
-    // Pipelined in chunks over two streams: the H2D copy of chunk c+1 and the D2H copy of
-    // chunk c-1 overlap the kernel of chunk c (pinned host buffers make the copies truly
-    // asynchronous; pageable ones still work, staged by the driver).
+    // Pipelined in chunks over two streams: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap
+    // the kernel of chunk c.  Pinned caller buffers are copied directly.  PAGEABLE caller buffers (MATLAB
+    // mxArrays, plain numpy) go through a pinned staging ring filled / drained by helper threads, so that the
+    // GPU copies stay asynchronous and the host memcpy's overlap the kernels too.
     const size_t per_in[4] = {(size_t)NX * 8, (size_t)nXN * 8, (size_t)nXN * 8, (size_t)nU * 8};
     const char* src[4] = {(const char*)x0, (const char*)x_ref, (const char*)x_lin, (const char*)u_lin};
     for (int i = 0; i < 4; ++i) CK(ctx->in[i].reserve(per_in[i] * B));
@@ -567,40 +702,142 @@ extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double d
     char* dst[8] = {(char*)u_opt, (char*)x_opt, (char*)exitflag, (char*)fval, (char*)slack_opt, (char*)iters,
                     (char*)workingSetB, (char*)workingSetC};
     for (int i = 0; i < 8; ++i) CK(ctx->out[i].reserve(per_out[i] * B));
-    const int nchunk = (B >= 16384) ? 8 : 1;
-    const int per = (B + nchunk - 1) / nchunk;
+    bool staged = false;
+    if (ctx->staging_mode != 1 && B >= 2048) {
+        staged = ctx->staging_mode == 2;
+        for (int i = 0; i < 4 && !staged; ++i) staged = is_pageable(src[i]);
+        for (int i = 0; i < 8 && !staged; ++i) staged = is_pageable(dst[i]);
+    }
+    ctx->last_host_path = staged ? 1 : 0;
+    // chunk size: pinned callers 1/8 of a large batch; staged callers 4096 problems (ring slot ~ 16 + 10 MB at N = 40)
+    const int per = staged ? (B >= 8192 ? 4096 : (B + 1) / 2) : (B >= 16384 ? (B + 7) / 8 : B);
+    const int nchunk = (B + per - 1) / per;
     if (nchunk > 1) {
         // stream2 starts after whatever is already queued on the main stream (ids upload)
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
         CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
     }
-    for (int c = 0; c < nchunk; ++c) {
-        const int lo = c * per, n = (lo + per <= B) ? per : B - lo;
-        if (n <= 0) break;
-        cudaStream_t st = (c & 1) ? ctx->stream2 : ctx->stream;
-        for (int i = 0; i < 4; ++i)
-            CK(cudaMemcpyAsync((char*)ctx->in[i].p + per_in[i] * lo, src[i] + per_in[i] * lo, per_in[i] * n,
-                               cudaMemcpyHostToDevice, st));
-        auto o = [&](int i) { return (char*)ctx->out[i].p + per_out[i] * lo; };
-        rc = fsae_ltvmpc_dev(ctx, model, n, N, dt, d_tid ? d_tid + lo : nullptr, d_pid ? d_pid + lo : nullptr,
-                             (const double*)((char*)ctx->in[0].p + per_in[0] * lo),
-                             (const double*)((char*)ctx->in[1].p + per_in[1] * lo),
-                             (const double*)((char*)ctx->in[2].p + per_in[2] * lo),
-                             (const double*)((char*)ctx->in[3].p + per_in[3] * lo),
-                             (double*)o(0), (double*)o(1), (int32_t*)o(2), (double*)o(3), (double*)o(4),
-                             iters ? (int32_t*)o(5) : nullptr, workingSetB ? (int8_t*)o(6) : nullptr,
-                             workingSetC ? (int8_t*)o(7) : nullptr, st);
-        if (rc) return rc;
-        for (int i = 0; i < 8; ++i)
-            if (dst[i]) CK(cudaMemcpyAsync(dst[i] + per_out[i] * lo, o(i), per_out[i] * n, cudaMemcpyDeviceToHost, st));
+    size_t off_in[5] = {0, 0, 0, 0, 0}, off_out[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) off_in[i + 1] = off_in[i] + ((per_in[i] * per + 63) & ~(size_t)63);
+    for (int i = 0; i < 8; ++i) off_out[i + 1] = off_out[i] + ((per_out[i] * per + 63) & ~(size_t)63);
+    std::vector<Latch> lat_in, lat_out;
+    if (staged) {
+        if (!ctx->copy_pool) {
+            ctx->copy_pool = new CopyPool();
+            ctx->copy_pool->start(ctx->copy_threads, ctx->device);
+        }
+        for (int r = 0; r < FSAE_RING; ++r) {
+            CK(ctx->ring_in[r].reserve(off_in[4]));
+            CK(ctx->ring_out[r].reserve(off_out[8]));
+        }
+        lat_in = std::vector<Latch>(nchunk);
+        lat_out = std::vector<Latch>(nchunk);
     }
+    const int T = ctx->copy_threads;
+    auto chunk_n = [&](int c) { const int lo = c * per; return (lo + per <= B) ? per : B - lo; };
+    // caller -> ring slot, split over the copy threads
+    auto post_in = [&](int c) {
+        const int lo = c * per, n = chunk_n(c), slot = c % FSAE_RING;
+        lat_in[c].reset(4 * T);
+        for (int i = 0; i < 4; ++i) {
+            const size_t tot = per_in[i] * n, piece = ((tot + T - 1) / T + 63) & ~(size_t)63;
+            for (int t = 0; t < T; ++t) {
+                const size_t o = (size_t)t * piece, len = o >= tot ? 0 : (o + piece <= tot ? piece : tot - o);
+                CopyJob j;
+                j.dst = ctx->ring_in[slot].p + off_in[i] + o;
+                j.src = src[i] + per_in[i] * lo + o;
+                j.bytes = len;
+                j.done = &lat_in[c];
+                ctx->copy_pool->post(j);
+            }
+        }
+    };
+    // ring slot -> caller, after the chunk's D2H copies (event of the slot)
+    auto post_out = [&](int c) {
+        const int lo = c * per, n = chunk_n(c), slot = c % FSAE_RING;
+        int njobs = 0;
+        for (int i = 0; i < 8; ++i) njobs += dst[i] ? T : 0;
+        lat_out[c].reset(njobs);
+        for (int i = 0; i < 8; ++i) {
+            if (!dst[i]) continue;
+            const size_t tot = per_out[i] * n, piece = ((tot + T - 1) / T + 63) & ~(size_t)63;
+            for (int t = 0; t < T; ++t) {
+                const size_t o = (size_t)t * piece, len = o >= tot ? 0 : (o + piece <= tot ? piece : tot - o);
+                CopyJob j;
+                j.dst = dst[i] + per_out[i] * lo + o;
+                j.src = ctx->ring_out[slot].p + off_out[i] + o;
+                j.bytes = len;
+                j.after = ctx->ev_ring[slot];
+                j.done = &lat_out[c];
+                ctx->copy_pool->post(j);
+            }
+        }
+    };
+    constexpr int AHEAD = 2;            // chunks staged ahead of the one being enqueued
+    int fail_rc = FSAE_OK;
+    if (staged)
+        for (int c = 0; c < AHEAD && c < nchunk; ++c) post_in(c);
+    for (int c = 0; c < nchunk; ++c) {
+        const int lo = c * per, n = chunk_n(c), slot = c % FSAE_RING;
+        cudaStream_t st = (c & 1) ? ctx->stream2 : ctx->stream;
+        if (staged) lat_in[c].wait();
+        if (fail_rc == FSAE_OK) {
+            auto ck = [&](cudaError_t e, const char* what) {
+                if (e != cudaSuccess && fail_rc == FSAE_OK) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); fail_rc = FSAE_ERR_CUDA; }
+            };
+            for (int i = 0; i < 4; ++i)
+                ck(cudaMemcpyAsync((char*)ctx->in[i].p + per_in[i] * lo,
+                                   staged ? ctx->ring_in[slot].p + off_in[i] : src[i] + per_in[i] * lo, per_in[i] * n,
+                                   cudaMemcpyHostToDevice, st), "H2D");
+            auto o = [&](int i) { return (char*)ctx->out[i].p + per_out[i] * lo; };
+            if (fail_rc == FSAE_OK) {
+                rc = fsae_ltvmpc_dev(ctx, model, n, N, dt, d_tid ? d_tid + lo : nullptr, d_pid ? d_pid + lo : nullptr,
+                                     (const double*)((char*)ctx->in[0].p + per_in[0] * lo),
+                                     (const double*)((char*)ctx->in[1].p + per_in[1] * lo),
+                                     (const double*)((char*)ctx->in[2].p + per_in[2] * lo),
+                                     (const double*)((char*)ctx->in[3].p + per_in[3] * lo),
+                                     (double*)o(0), (double*)o(1), (int32_t*)o(2), (double*)o(3), (double*)o(4),
+                                     iters ? (int32_t*)o(5) : nullptr, workingSetB ? (int8_t*)o(6) : nullptr,
+                                     workingSetC ? (int8_t*)o(7) : nullptr, st);
+                if (rc) fail_rc = rc;
+            }
+            for (int i = 0; i < 8 && fail_rc == FSAE_OK; ++i)
+                if (dst[i])
+                    ck(cudaMemcpyAsync(staged ? ctx->ring_out[slot].p + off_out[i] : dst[i] + per_out[i] * lo, o(i),
+                                       per_out[i] * n, cudaMemcpyDeviceToHost, st), "D2H");
+        }
+        if (staged) {
+            // the slot's event is recorded even after a failure so that no copy thread waits forever
+            cudaEventRecord(ctx->ev_ring[slot], st);
+            post_out(c);
+            // stage chunk c + AHEAD: its ring slot was used by chunk c + AHEAD - RING, which must be delivered
+            const int nx = c + AHEAD;
+            if (nx < nchunk) {
+                if (nx - FSAE_RING >= 0) lat_out[nx - FSAE_RING].wait();
+                post_in(nx);
+            }
+        }
+    }
+    if (staged)
+        for (int c = 0; c < nchunk; ++c) lat_out[c].wait();
     if (nchunk > 1) {
         CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    return FSAE_OK;
+    return fail_rc;
 }
+
+// Host-path selection of the _host entry points (tests / bench): 0 = automatic (pinned staging ring when a
+// caller buffer is pageable), 1 = always direct copies, 2 = always the staging ring.  Returns the previous mode.
+extern "C" int fsae_set_host_staging(fsae_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 2) return FSAE_ERR_ARG;
+    const int old = ctx->staging_mode;
+    ctx->staging_mode = mode;
+    return old;
+}
+// 1 if the most recent fsae_ltvmpc_host call went through the staging ring, 0 if it copied directly
+extern "C" int fsae_last_host_path(const fsae_ctx* ctx) { return ctx ? ctx->last_host_path : -1; }
 
 // merge exit flags / iteration counts across SQP passes
 __global__ void sqp_merge_kernel(int B, const int32_t* ef_pass, const int32_t* it_pass, int32_t* ef_acc, int32_t* it_acc, int first) {

@@ -166,6 +166,15 @@ int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N_steps, double dt,
                     double* slack_opt, int32_t* iters,
                     int8_t* workingSetB, int8_t* workingSetC, void* stream);
 
+/* Host-path selection of the _host entry points.  Pinned caller buffers (cudaHostAlloc / cudaHostRegister)
+ * are copied directly.  PAGEABLE caller buffers -- what a MEX gateway gets from mxGetPr() -- go through a
+ * pinned staging ring inside the library, filled and drained by helper threads (FSAE_COPY_THREADS, default
+ * min(4, cores/2)), so that the PCIe copies stay asynchronous and overlap the kernels.
+ * mode 0 = automatic (default), 1 = always direct copies, 2 = always the staging ring; returns the previous mode. */
+int fsae_set_host_staging(fsae_ctx* ctx, int mode);
+/* 1 if the most recent fsae_ltvmpc_host call used the staging ring, 0 if it copied directly. */
+int fsae_last_host_path(const fsae_ctx* ctx);
+
 /* ---- sequential QP: n_sqp repeated relinearise + condense + QP passes per problem, each
  * pass linearising at the previous pass's (x_opt, u_opt) -- BASELINE.json configs[3]
  * ("mpc/nonlinear SQP: repeated relinearise+QP iterations per step").  It is exactly what

@@ -28,7 +28,7 @@ class MatlabError(Exception):
 TOKEN_RE = re.compile(r"""
     (?P<num>(\d+(\.(?![*/\\^'])\d*)?([eE][+-]?\d+)?|\.\d+([eE][+-]?\d+)?))
   | (?P<id>[A-Za-z_]\w*)
-  | (?P<op>\.\*|\./|\.\^|\.'|==|~=|<=|>=|&&|\|\||[-+*/\\^'<>=&|~:,;()\[\]{}@])
+  | (?P<op>\.\*|\./|\.\^|\.'|==|~=|<=|>=|&&|\|\||\.(?=[A-Za-z_])|[-+*/\\^'<>=&|~:,;()\[\]{}@])
 """, re.X)
 
 KEYWORDS = {"function", "end", "if", "elseif", "else", "for", "while", "break", "continue", "return"}
@@ -403,6 +403,9 @@ class Parser:
             elif tok.kind == "op" and tok.val in ("'", ".'") and not (in_matrix and tok.sp):
                 self.next()
                 node = ("transpose", node)
+            elif tok.kind == "op" and tok.val == ".":
+                self.next()                      # struct field s.name (parsed; only dict values can be read)
+                node = ("field", node, self.next().val)
             else:
                 return node
 
@@ -584,6 +587,20 @@ class Matlab:
         self.cache[name] = None
         return None
 
+    def run_script_lines(self, path, first, last, env):
+        """Execute lines first..last (1-based, inclusive) of a SCRIPT file in the workspace `env`
+        (a dict that is updated in place), e.g. a block of main.m.  Returns env."""
+        with open(path) as fh:
+            lines = fh.read().split("\n")
+        src = "\n".join(lines[first - 1:last]) + "\n"
+        stmts = Parser(tokenize(src)).parse_block(("eof",))
+        frame = Frame(self, env, {})
+        try:
+            frame.run(stmts)
+        except (Break, Return):
+            pass
+        return env
+
     def call(self, name, *args, nargout=1):
         fn = self.overrides.get(name) or self.load(name)
         if fn is None:
@@ -668,6 +685,16 @@ class Frame:
                 cur = np.zeros((0, 0))
             cur = M(cur)
             self.env[name] = self.index_assign(cur, target[2], M(val))
+            return
+        if target[0] == "cellindex" and target[1][0] == "name":
+            # c{k} = v on a cell array held as a python list (value semantics: copy on write)
+            name = target[1][1]
+            cur = list(self.env.get(name) or [])
+            idx = int(scalar(self.eval(target[2][0]))) - 1
+            while len(cur) <= idx:
+                cur.append(np.zeros((0, 0)))
+            cur[idx] = val
+            self.env[name] = cur
             return
         raise MatlabError(f"unsupported assignment target {target[0]}")
 
@@ -873,6 +900,11 @@ class Frame:
             return target[idx]
         if k == "cell":
             return [self.eval(e) for row in node[1] for e in row]
+        if k == "field":
+            target = self.eval(node[1])
+            if not isinstance(target, dict) or node[2] not in target:
+                raise MatlabError(f"no field {node[2]!r}")
+            return target[node[2]]
         if k == "transpose":
             v = M(self.eval(node[1]))
             return v.T.copy()
@@ -884,7 +916,10 @@ class Frame:
                 return v
             return ~(v != 0)
         if k == "bin":
-            return self.binop(node[1], M(self.eval(node[2])), M(self.eval(node[3])))
+            lhs, rhs = self.eval(node[2]), self.eval(node[3])
+            if isinstance(lhs, str) or isinstance(rhs, str):
+                return self.string_binop(node[1], lhs, rhs)
+            return self.binop(node[1], M(lhs), M(rhs))
         if k == "andand":
             return np.array([[is_true(self.eval(node[1])) and is_true(self.eval(node[2]))]])
         if k == "oror":
@@ -924,6 +959,23 @@ class Frame:
             name = node[1]
             return lambda *args, nargout=1: self.call_function(name, list(args), nargout)
         raise MatlabError(f"cannot evaluate {k}")
+
+    @staticmethod
+    def string_binop(op, a, b):
+        """string scalars ("..."): comparison gives a logical scalar, + concatenates (numbers are
+        converted the way MATLAB's string() prints integers)"""
+        def txt(v):
+            if isinstance(v, str):
+                return v
+            f = float(scalar(v))
+            return str(int(f)) if f == int(f) else repr(f)
+        if op == "==":
+            return np.array([[isinstance(a, str) and isinstance(b, str) and a == b]])
+        if op == "~=":
+            return np.array([[not (isinstance(a, str) and isinstance(b, str) and a == b)]])
+        if op == "+":
+            return txt(a) + txt(b)
+        raise MatlabError(f"unsupported string operator {op}")
 
     def binop(self, op, a, b):
         a = a.astype(np.float64) if a.dtype == bool and op not in ("&", "|") else a
@@ -1142,7 +1194,25 @@ def b_numel(fr, args, no):
     return np.array([[float(M(args[0]).size)]])
 
 
+def b_angdiff(fr, args, no):
+    """Robotics System Toolbox angdiff(alpha, beta): beta - alpha wrapped to [-pi, pi]
+    (wrapToPi: values already inside the interval are returned unchanged; outside it
+    mod(theta + pi, 2 pi) - pi, with positive multiples of 2 pi mapped to +pi)."""
+    if len(args) != 2:
+        raise MatlabError("angdiff: two-argument form only")
+    th = M(args[1]).astype(np.float64) - M(args[0]).astype(np.float64)
+    out = th.copy()
+    pos = (th < -math.pi) | (th > math.pi)
+    t2 = th[pos] + math.pi
+    w = t2 - np.floor(t2 / (2 * math.pi)) * (2 * math.pi)
+    w[(w == 0) & (t2 > 0)] = 2 * math.pi
+    out[pos] = w - math.pi
+    return out
+
+
 BUILTINS = {
+    "angdiff": b_angdiff,
+    "tic": lambda fr, a, no: [], "toc": lambda fr, a, no: np.array([[0.0]]),
     "zeros": b_zeros(0.0), "ones": b_zeros(1.0), "eye": b_eye, "inf": b_inf, "Inf": b_inf,
     "pi": lambda fr, a, no: np.array([[math.pi]]),
     "size": b_size, "length": b_length, "numel": b_numel, "repmat": b_repmat, "spdiags": b_spdiags,
