@@ -76,22 +76,24 @@ SIGNATURES = {
     "fsae_last_host_path": (C.c_int, [_ctx]),
 }
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """Load libfsae_mpc_b200.so (build it with `python -m fsae_mpc_b200.build`)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load(path=None):
+    """Load libfsae_mpc_b200.so (build it with `python -m fsae_mpc_b200.build`).  `path` (or the environment
+    variable FSAE_LIB) selects another build of the same C-ABI, e.g. the cross-check library
+    libfsae_mpc_b200_xcheck.so that the tests use for fsae_debug_set_kernel_version."""
+    path = path or os.environ.get("FSAE_LIB") or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: the CUDA extension was not built "
+            f"{path} is missing: the CUDA extension was not built "
             "(python -m fsae_mpc_b200.build).  fsae_mpc_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    _libs[path] = lib
     return lib

@@ -76,8 +76,8 @@ def default_params(model=KINEMATIC):
 class FsaeMpc:
     """One context = one GPU + one stream + its track / parameter tables."""
 
-    def __init__(self, device=0):
-        self._lib = _lib.load()
+    def __init__(self, device=0, lib_path=None):
+        self._lib = _lib.load(lib_path)
         self._ctx = C.c_void_p()
         rc = self._lib.fsae_create(C.byref(self._ctx), int(device))
         if rc != 0:
@@ -314,6 +314,16 @@ class FsaeMpc:
         operator M = [e_slack | J] of every problem (fsae_debug_set_taps; tests)."""
         self._check(self._lib.fsae_debug_set_taps(self._ctx, C.c_void_p(d_H or None), C.c_void_p(d_g or None),
                                                   C.c_void_p(d_M or None)), "fsae_debug_set_taps")
+
+    def set_host_staging(self, mode):
+        """Host path of the _host calls: 0 automatic (pinned staging ring when a caller buffer is pageable),
+        1 always direct copies, 2 always the ring.  Returns the previous mode."""
+        return int(self._lib.fsae_set_host_staging(self._ctx, int(mode)))
+
+    @property
+    def last_host_path(self):
+        """1 if the last fused-step host call went through the pinned staging ring, else 0."""
+        return int(self._lib.fsae_last_host_path(self._ctx))
 
     def set_kernel_version(self, v):
         """2 = register-tiled product kernel (default), 1 = shared-memory cross-check variant."""

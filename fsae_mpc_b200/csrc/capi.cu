@@ -14,8 +14,7 @@
 #include <vector>
 
 #include "../../include/fsae_mpc_b200.h"
-#include "fused_v1.cuh"
-#include "fused_v2.cuh"
+#include "launch.h"
 #include "staged.cuh"
 #include "probe.cuh"
 #include "dense_qp.cuh"
@@ -65,8 +64,8 @@ struct PinBuf {
 
 // Helper threads that move data between the caller's PAGEABLE buffers and the pinned staging ring
 // (MATLAB's mxArrays and plain numpy arrays are pageable: a cudaMemcpyAsync on them is staged by the
-// driver on the calling thread and serialises with everything else).  A job is one memcpy, optionally
-// after a CUDA event (the D2H copy of a chunk into the ring); a latch counts a group of jobs down.
+// driver on the calling thread and serialises with everything else).  A job is one memcpy; a latch
+// counts a group of jobs down.
 struct Latch {
     std::mutex mu;
     std::condition_variable cv;
@@ -79,7 +78,6 @@ struct CopyJob {
     char* dst = nullptr;
     const char* src = nullptr;
     size_t bytes = 0;
-    cudaEvent_t after = nullptr;
     Latch* done = nullptr;
 };
 struct CopyPool {
@@ -104,7 +102,6 @@ struct CopyPool {
                 j = q.front();
                 q.pop_front();
             }
-            if (j.after) cudaEventSynchronize(j.after);
             if (j.bytes) memcpy(j.dst, j.src, j.bytes);
             if (j.done) j.done->count_down();
         }
@@ -122,7 +119,7 @@ struct CopyPool {
     ~CopyPool() { shutdown(); }
 };
 
-constexpr int FSAE_RING = 4;        // slots of the pinned staging ring
+constexpr int FSAE_RING = 6;        // slots of the pinned staging ring
 
 struct fsae_ctx {
     int device = 0;
@@ -147,7 +144,7 @@ struct fsae_ctx {
     std::vector<Slab> slabs;   // per-problem L2 slabs of the long-horizon kernels, one pool PER STREAM
     // pageable callers: pinned staging ring + copy threads (created on first use)
     PinBuf ring_in[FSAE_RING], ring_out[FSAE_RING];
-    cudaEvent_t ev_ring[FSAE_RING] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_ring[FSAE_RING] = {};
     CopyPool* copy_pool = nullptr;
     int copy_threads = 0;
     int staging_mode = 0;      // 0 auto (stage when a caller buffer is pageable), 1 never, 2 always
@@ -253,10 +250,10 @@ extern "C" int fsae_create(fsae_ctx** out, int device) {
     if (cudaMemcpy(ctx->d_params, ctx->h_params, sizeof(ctx->h_params), cudaMemcpyHostToDevice) != cudaSuccess)
         return fail("memcpy params");
     {
-        // copy threads of the pageable-host path: FSAE_COPY_THREADS, default min(4, cores / 2)
+        // copy threads of the pageable-host path: FSAE_COPY_THREADS, default min(8, cores / 2)
         const char* e = getenv("FSAE_COPY_THREADS");
         int t = e ? atoi(e) : 0;
-        if (t <= 0) { t = (int)std::thread::hardware_concurrency() / 2; if (t > 4) t = 4; }
+        if (t <= 0) { t = (int)std::thread::hardware_concurrency() / 2; if (t > 8) t = 8; }
         ctx->copy_threads = t < 1 ? 1 : (t > 16 ? 16 : t);
     }
     *out = ctx;
@@ -502,93 +499,21 @@ static DevBuf& slab_pool(fsae_ctx* ctx, cudaStream_t st) {
     return ctx->slabs.back().buf;
 }
 
-template <class Model, int N, int NT>
-static int launch_fused_v1(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
-    using S_t = SmemV1<Model, N, NT>;
-    auto kern = ltvmpc_fused_v1_kernel<Model, N, NT>;
-    static bool configured[64] = {false};
-    if (!configured[ctx->device & 63]) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S_t)));
-        configured[ctx->device & 63] = true;
-    }
-    kern<<<a.B, NT, sizeof(S_t), st>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return FSAE_OK;
-}
-
-// Long horizons (nV > 95: the operator no longer fits one CTA's registers or shared memory):
-// the shared-memory kernel variant with the operator in a per-CTA global slab that stays
-// L2-resident (<= 148 CTAs x 207 KB in flight).  Launched in slices so the slab pool is bounded.
-template <class Model, int N>
-static int launch_fused_long(fsae_ctx* ctx, BatchArgs a, cudaStream_t st) {
-    using S_t = SmemV1<Model, N, 256, true>;
-    using D = Dims<Model, N>;
-    auto kern = ltvmpc_fused_v1_kernel<Model, N, 256, true>;
-    static bool configured[64] = {false};
-    if (!configured[ctx->device & 63]) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S_t)));
-        configured[ctx->device & 63] = true;
-    }
-    constexpr int SLICE = 2048;
-    DevBuf& pool = slab_pool(ctx, st);
-    const int nsl = a.B < SLICE ? a.B : SLICE;
-    CK(pool.reserve((size_t)nsl * D::nV * D::LD * sizeof(double)));
-    const int B = a.B;
-    constexpr int NX = Model::NX, NU = Model::NU, NS = Model::NS, nU = NU * N, nV = nU + NS;
-    const int nC = Cons<Model>::n_ref_rows(N);
-    for (int lo = 0; lo < B; lo += SLICE) {
-        BatchArgs c = a;
-        c.B = (lo + SLICE <= B) ? SLICE : B - lo;
-        c.m_scratch = (double*)pool.p;
-        if (a.track_id) c.track_id = a.track_id + lo;
-        if (a.param_id) c.param_id = a.param_id + lo;
-        c.x0 = a.x0 + (size_t)lo * NX; c.x_ref = a.x_ref + (size_t)lo * NX * N;
-        c.x_lin = a.x_lin + (size_t)lo * NX * N; c.u_lin = a.u_lin + (size_t)lo * NU * N;
-        c.u_opt = a.u_opt + (size_t)lo * nU; c.x_opt = a.x_opt + (size_t)lo * NX * N;
-        c.exitflag = a.exitflag + lo; c.fval = a.fval + lo; c.slack_opt = a.slack_opt + (size_t)lo * NS;
-        if (a.iters) c.iters = a.iters + lo;
-        if (a.wsB) c.wsB = a.wsB + (size_t)lo * nV;
-        if (a.wsC) c.wsC = a.wsC + (size_t)lo * nC;
-        kern<<<c.B, 256, sizeof(S_t), st>>>(c);
+// One launch, or -- for kernels that keep part of their state in a per-problem global slab (long horizons: the
+// slab stays L2-resident with <= 148 CTAs in flight) -- slices of SLICE problems so that the slab pool is bounded.
+typedef cudaError_t (*fused_launch_fn)(const BatchArgs&, cudaStream_t, int);
+static int launch_fused(fsae_ctx* ctx, BatchArgs a, cudaStream_t st, fused_launch_fn fn, int variant, size_t slab_doubles,
+                        int NX, int NU, int NS, int nC) {
+    if (slab_doubles == 0) {
+        CK(fn(a, st, variant));
         ctx->launches++;
-        CK(cudaGetLastError());
+        return FSAE_OK;
     }
-    return FSAE_OK;
-}
-
-template <class Model, int N, int MINB, int NW = 8, int KB = 1, int CSR = -1>
-static int launch_fused_v2(fsae_ctx* ctx, const BatchArgs& a, cudaStream_t st) {
-    using S_t = SmemV2<Model, N, NW, KB, CSR>;
-    // the occupancy the kernel was tuned for must survive every change of the shared-memory layout:
-    // 228 KB per SM, 1 KB reserved per resident CTA
-    static_assert((size_t)MINB * (sizeof(S_t) + 1024) <= 233472, "MINB CTAs per SM no longer fit shared memory");
-    auto kern = ltvmpc_fused_v2_kernel<Model, N, MINB, NW, KB, CSR>;
-    static bool configured[64] = {false};
-    if (!configured[ctx->device & 63]) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S_t)));
-        configured[ctx->device & 63] = true;
-    }
-    kern<<<a.B, 32 * NW, sizeof(S_t), st>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return FSAE_OK;
-}
-
-// Long horizons with the register-tiled kernel: NW warps, CSR of the column slots of the operator tile in
-// registers and the rest in shared memory; B_bar rows the constraints do not touch, the packed H and the
-// J staging in a per-problem global slab (L2-resident: <= 148 CTAs x 260 KB in flight).  Launched in
-// slices so the slab pool is bounded.
-template <class Model, int N, int NW, int CSR>
-static int launch_fused_v2_long(fsae_ctx* ctx, BatchArgs a, cudaStream_t st) {
-    using S_t = SmemV2<Model, N, NW, 1, CSR>;
     constexpr int SLICE = 2048;
     DevBuf& pool = slab_pool(ctx, st);
     const int nsl = a.B < SLICE ? a.B : SLICE;
-    CK(pool.reserve((size_t)nsl * S_t::SLAB * sizeof(double)));
-    const int B = a.B;
-    constexpr int NX = Model::NX, NU = Model::NU, NS = Model::NS, nU = NU * N, nV = nU + NS;
-    const int nC = Cons<Model>::n_ref_rows(N);
+    CK(pool.reserve((size_t)nsl * slab_doubles * sizeof(double)));
+    const int B = a.B, N = a.N, nU = NU * N, nV = nU + NS;
     for (int lo = 0; lo < B; lo += SLICE) {
         BatchArgs c = a;
         c.B = (lo + SLICE <= B) ? SLICE : B - lo;
@@ -602,11 +527,16 @@ static int launch_fused_v2_long(fsae_ctx* ctx, BatchArgs a, cudaStream_t st) {
         if (a.iters) c.iters = a.iters + lo;
         if (a.wsB) c.wsB = a.wsB + (size_t)lo * nV;
         if (a.wsC) c.wsC = a.wsC + (size_t)lo * nC;
-        const int rc = launch_fused_v2<Model, N, 1, NW, 1, CSR>(ctx, c, st);
-        if (rc != FSAE_OK) return rc;
+        CK(fn(c, st, variant));
+        ctx->launches++;
     }
     return FSAE_OK;
 }
+#ifdef FSAE_XCHECK
+static cudaError_t launch_v1_20(const BatchArgs& a, cudaStream_t st, int) { return launch_v1_kin(20, a, st); }
+static cudaError_t launch_v1_40(const BatchArgs& a, cudaStream_t st, int) { return launch_v1_kin(40, a, st); }
+static cudaError_t launch_v1_80(const BatchArgs& a, cudaStream_t st, int) { return launch_v1_kin(80, a, st); }
+#endif
 
 extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt,
                                const int32_t* track_id, const int32_t* param_id,
@@ -635,26 +565,22 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
     a.dbg_H = ctx->tap_H; a.dbg_g = ctx->tap_g; a.dbg_M = ctx->tap_M;
     CK(cudaEventRecord(ctx->ev0, st));
     int rc = FSAE_ERR_UNSUPPORTED;
+    const int kv = ctx->kernel_version;     // 2 = product kernel; others only in the cross-check build
+    const int nC = (model == FSAE_MODEL_KINEMATIC) ? 6 * N : 20 * N;
     if (model == FSAE_MODEL_KINEMATIC) {
-        const bool v1 = ctx->kernel_version == 1;
-        // tuning / cross-check switch (fsae_debug_set_kernel_version): warp count x block size variants
-        const int kv = ctx->kernel_version;
-        if (N == 40) rc = v1 ? launch_fused_v1<KinModel, 40, 256>(ctx, a, st)
-                     : kv == 21 ? launch_fused_v2<KinModel, 40, 1, 8, 1>(ctx, a, st)     // 8 warps (1 CTA/SM: shared memory)
-                     : kv == 26 ? launch_fused_v2<KinModel, 40, 2, 6, 2>(ctx, a, st)     // 6 warps, blocks of 2 constraints per search
-                     : kv == 28 ? launch_fused_v2<KinModel, 40, 2, 6, 3>(ctx, a, st)     // 6 warps, blocks of 3
-                     : kv == 29 ? launch_fused_v2<KinModel, 40, 2, 4, 1>(ctx, a, st)     // 4 warps
-                     : launch_fused_v2<KinModel, 40, 2, 6, 1>(ctx, a, st);               // product: 6 warps, one constraint per search
-        else if (N == 20) rc = v1 ? launch_fused_v1<KinModel, 20, 256>(ctx, a, st)
-                          : kv == 21 ? launch_fused_v2<KinModel, 20, 2, 8, 1>(ctx, a, st)      // 8 warps x 2 CTAs/SM: 3.36M QP/s
-                          : kv == 26 ? launch_fused_v2<KinModel, 20, 3, 6, 1>(ctx, a, st)      // 6 warps x 3: 4.39M
-                          : launch_fused_v2<KinModel, 20, 5, 4, 1>(ctx, a, st);                // 4 warps x 5 CTAs/SM: 4.63M (13 KB operator)
-        else if (N == 80) rc = v1 ? launch_fused_long<KinModel, 80>(ctx, a, st)          // operator in an L2 slab (cross-check)
-                          : launch_fused_v2_long<KinModel, 80, 12, 4>(ctx, a, st);  // 12 warps, 4 of 6 column slots in registers
+#ifdef FSAE_XCHECK
+        if (kv == 1 && (N == 20 || N == 40 || N == 80))
+            rc = launch_fused(ctx, a, st, N == 20 ? launch_v1_20 : (N == 40 ? launch_v1_40 : launch_v1_80), kv,
+                              N == 80 ? slab_v1_kin80() : 0, NX, NU, NS, nC);
+        else
+#endif
+        if (N == 40) rc = launch_fused(ctx, a, st, launch_kin40, kv, 0, NX, NU, NS, nC);
+        else if (N == 20) rc = launch_fused(ctx, a, st, launch_kin20, kv, 0, NX, NU, NS, nC);
+        else if (N == 80) rc = launch_fused(ctx, a, st, launch_kin80, kv, slab_kin80(), NX, NU, NS, nC);
         else ctx->err = "kinematic fused step: horizon must be 20, 40 or 80";
     } else {
-        if (N == 40) rc = launch_fused_v2<DynModel, 40, 1>(ctx, a, st);
-        else if (N == 20) rc = launch_fused_v2<DynModel, 20, 1>(ctx, a, st);
+        if (N == 40) rc = launch_fused(ctx, a, st, launch_dyn40, kv, 0, NX, NU, NS, nC);
+        else if (N == 20) rc = launch_fused(ctx, a, st, launch_dyn20, kv, 0, NX, NU, NS, nC);
         else ctx->err = "dynamic fused step: horizon must be 20 or 40";
     }
     if (rc != FSAE_OK) return rc;
@@ -752,7 +678,8 @@ extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double d
             }
         }
     };
-    // ring slot -> caller, after the chunk's D2H copies (event of the slot)
+    // ring slot -> caller; posted by the main thread once the chunk's D2H copies have completed, so every job in
+    // the queue is runnable (a job that waited on an event would block the copy-in jobs queued behind it)
     auto post_out = [&](int c) {
         const int lo = c * per, n = chunk_n(c), slot = c % FSAE_RING;
         int njobs = 0;
@@ -767,13 +694,13 @@ extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double d
                 j.dst = dst[i] + per_out[i] * lo + o;
                 j.src = ctx->ring_out[slot].p + off_out[i] + o;
                 j.bytes = len;
-                j.after = ctx->ev_ring[slot];
                 j.done = &lat_out[c];
                 ctx->copy_pool->post(j);
             }
         }
     };
-    constexpr int AHEAD = 2;            // chunks staged ahead of the one being enqueued
+    constexpr int AHEAD = 3;            // chunks staged ahead of the one being enqueued
+    static_assert(AHEAD < FSAE_RING, "ring depth");
     int fail_rc = FSAE_OK;
     if (staged)
         for (int c = 0; c < AHEAD && c < nchunk; ++c) post_in(c);
@@ -807,10 +734,13 @@ extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double d
                                        per_out[i] * n, cudaMemcpyDeviceToHost, st), "D2H");
         }
         if (staged) {
-            // the slot's event is recorded even after a failure so that no copy thread waits forever
             cudaEventRecord(ctx->ev_ring[slot], st);
-            post_out(c);
-            // stage chunk c + AHEAD: its ring slot was used by chunk c + AHEAD - RING, which must be delivered
+            // chunk c is queued on the GPU: now deliver chunk c - 1 (its event has fired or fires soon) ...
+            if (c >= 1) {
+                cudaEventSynchronize(ctx->ev_ring[(c - 1) % FSAE_RING]);
+                post_out(c - 1);
+            }
+            // ... and stage chunk c + AHEAD, whose ring slot was last used by chunk c + AHEAD - RING
             const int nx = c + AHEAD;
             if (nx < nchunk) {
                 if (nx - FSAE_RING >= 0) lat_out[nx - FSAE_RING].wait();
@@ -818,8 +748,11 @@ extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double d
             }
         }
     }
-    if (staged)
+    if (staged) {
+        cudaEventSynchronize(ctx->ev_ring[(nchunk - 1) % FSAE_RING]);
+        post_out(nchunk - 1);
         for (int c = 0; c < nchunk; ++c) lat_out[c].wait();
+    }
     if (nchunk > 1) {
         CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
@@ -1087,7 +1020,11 @@ extern "C" int fsae_debug_set_taps(fsae_ctx* ctx, double* d_H, double* d_g, doub
 
 // select the fused kernel variant (tests cross-check v1 against v2); returns the previous one
 extern "C" int fsae_debug_set_kernel_version(fsae_ctx* ctx, int v) {
+#ifdef FSAE_XCHECK
     if (!ctx || (v != 1 && v != 2 && v != 21 && v != 26 && v != 28 && v != 29)) return FSAE_ERR_ARG;
+#else
+    if (!ctx || v != 2) return FSAE_ERR_ARG;     // the product library carries the product kernel only
+#endif
     const int old = ctx->kernel_version;
     ctx->kernel_version = v;
     return old;

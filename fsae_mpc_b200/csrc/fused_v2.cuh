@@ -16,10 +16,16 @@
 // and J (J'HJ = I) as the closed-loop response to unit innovations, its rows produced by adjoint
 // threads that follow the recursion stage by stage.
 //
-// Pipeline and reference mapping: see fused_v1.cuh header (same stages).
+// Pipeline per CTA (reference function each stage replaces):
+//   load        x0, x_ref, x_lin, u_lin                      (arguments of ltvmpc_*_curvilinear.m:1)
+//   linearise   A_k, B_k, d_k per step                        (rk2_kinematic_curvilinear.m:25-50 ...)
+//   discretise  A_k*dt+I, B*dt, d*dt, free response           (sequential_integration.m:16-18,21-26,38-47)
+//   condense    packed B_bar rows, H, g, row bounds           (sequential_integration.m:28-36,
+//                                                              *_state_constraints.m, generate_qp.m:23-33)
+//   solve       Goldfarb-Idnani dual active set, operator form (qpOASES call, ltvmpc_*_curvilinear.m:52)
+//   output      u_opt, slack_opt, x_opt, fval, exitflag       (ltvmpc_*_curvilinear.m:57-60)
 #pragma once
-#include "cons.cuh"
-#include "fused_v1.cuh"   // BatchArgs, Dims
+#include "batch.cuh"   // BatchArgs, Dims
 #include "gi_core.cuh"
 
 namespace fsae {

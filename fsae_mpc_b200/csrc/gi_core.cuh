@@ -387,7 +387,10 @@ struct GiOps {
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) {
                     const int i = row0 + r;
-                    m(r, s) = (j < ns) ? ((i == nC + j) ? 1.0 : 0.0) : (j < nV ? t[r][s] : 0.0);
+                    // K1 column of a flat variable that starts on its bound: N'K1 = I with the normal
+                    // +e_i at a lower bound (x_i >= lb) and -e_i at an upper bound (-x_i >= -ub)
+                    const double sgn = (j < ns && (S.act[j < ns ? j : 0] & 1)) ? -1.0 : 1.0;
+                    m(r, s) = (j < ns) ? ((i == nC + j) ? sgn : 0.0) : (j < nV ? t[r][s] : 0.0);
                 }
             }
         }
@@ -432,6 +435,7 @@ struct GiOps {
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row0 = warp * RPW;
         GiStats st = {0, GI_EXIT_SOLVED, 0, 0, 0};
         int rbuf = 0, drops_at_refresh = 0;
+        bool refresh_failed = false;
         PHASE_DECL;
         // drop working-set column l: K1 <- K1 + k r'^T with r' = -K1' H k / k'Hk (k = column l), the freed
         // direction k / sqrt(k'Hk) joins J2 as column q-1, column q-1 of K1 moves into slot l
@@ -580,10 +584,14 @@ struct GiOps {
                         ymax = -dkey_inv(km);
                     }
                     __syncthreads();                   // x complete
-                    if (!(ymin < -1e-10 * (1.0 + ymax)) || pass >= 8 || ++st.iters > max_iter) break;
+                    if (!(ymin < -1e-10 * (1.0 + ymax))) break;
+                    // a multiplier is still negative: the point is primal feasible but not optimal.  Out of
+                    // passes / iterations that is qpOASES's "maximum number of iterations" (exitflag 1), not success.
+                    if (pass >= 8 || ++st.iters > max_iter) { st.exitflag = GI_EXIT_MAXITER; refresh_failed = true; break; }
                     drop_column(lmin);
                     drops_at_refresh = st.n_drop;
                 }
+                if (refresh_failed) break;
                 continue;
             }
             int nleft = 0;                          // candidates (sorted by violation: a prefix is valid)

@@ -1,0 +1,15 @@
+// Kinematic model, horizon 20: 4 warps x 5 CTAs/SM (13 KB operator).
+#include "launch_impl.cuh"
+namespace fsae {
+cudaError_t launch_kin20(const BatchArgs& a, cudaStream_t st, int variant) {
+#ifdef FSAE_XCHECK
+    switch (variant) {
+        case 21: return launch_v2<KinModel, 20, 2, 8, 1>(a, st);     // 8 warps x 2 CTAs/SM: 3.36M QP/s
+        case 26: return launch_v2<KinModel, 20, 3, 6, 1>(a, st);     // 6 warps x 3: 4.39M
+        default: break;
+    }
+#endif
+    (void)variant;
+    return launch_v2<KinModel, 20, 5, 4, 1>(a, st);                  // 4 warps x 5 CTAs/SM: 4.63M
+}
+}  // namespace fsae

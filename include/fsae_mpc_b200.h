@@ -169,7 +169,7 @@ int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N_steps, double dt,
 /* Host-path selection of the _host entry points.  Pinned caller buffers (cudaHostAlloc / cudaHostRegister)
  * are copied directly.  PAGEABLE caller buffers -- what a MEX gateway gets from mxGetPr() -- go through a
  * pinned staging ring inside the library, filled and drained by helper threads (FSAE_COPY_THREADS, default
- * min(4, cores/2)), so that the PCIe copies stay asynchronous and overlap the kernels.
+ * min(8, cores/2)), so that the PCIe copies stay asynchronous and overlap the kernels.
  * mode 0 = automatic (default), 1 = always direct copies, 2 = always the staging ring; returns the previous mode. */
 int fsae_set_host_staging(fsae_ctx* ctx, int mode);
 /* 1 if the most recent fsae_ltvmpc_host call used the staging ring, 0 if it copied directly. */

@@ -6,12 +6,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 prof_so = os.path.join(ROOT, "build", "libfsae_prof.so")
-if not os.path.exists(prof_so) or os.path.getmtime(prof_so) < max(os.path.getmtime(os.path.join(ROOT, "fsae_mpc_b200", "csrc", f)) for f in os.listdir(os.path.join(ROOT, "fsae_mpc_b200", "csrc"))):
+CSRC = os.path.join(ROOT, "fsae_mpc_b200", "csrc")
+if not os.path.exists(prof_so) or os.path.getmtime(prof_so) < max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC)):
+    # the phase counters are __device__ globals: the profile build is ONE translation unit (all TUs included)
     os.makedirs(os.path.dirname(prof_so), exist_ok=True)
-    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DFSAE_PROFILE", "-shared",
-                    "-Xcompiler", "-fPIC", "-o", prof_so, os.path.join(ROOT, "fsae_mpc_b200", "csrc", "capi.cu")], check=True)
-from fsae_mpc_b200 import _lib
-_lib.LIB_PATH = prof_so
+    unity = os.path.join(ROOT, "build", "prof_unity.cu")
+    with open(unity, "w") as fh:
+        fh.write("".join(f'#include "{os.path.join(CSRC, f)}"\n' for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")))
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DFSAE_PROFILE", "-DFSAE_XCHECK",
+                    "-diag-suppress", "128,39", "-shared", "-Xcompiler", "-fPIC", "-o", prof_so, unity], check=True)
+os.environ["FSAE_LIB"] = prof_so
 import fsae_mpc_b200 as fm
 from fsae_mpc_b200 import workload as wl
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 296

@@ -54,6 +54,20 @@ def fso():
 
 
 @pytest.fixture(scope="session")
+def mpc_x():
+    """Context on the CROSS-CHECK build of the library (libfsae_mpc_b200_xcheck.so: product kernels plus the
+    shared-memory operator kernel and the warp-count / block-size variants) for the variant-agreement tests."""
+    import fsae_mpc_b200 as fm
+    from fsae_mpc_b200 import build
+    ctx = fm.FsaeMpc(0, lib_path=build.LIB_XCHECK)
+    t = load_golden("tracks.npz")
+    for tid, name in enumerate(("fsg2019", "fss2019", "fso2020")):
+        ctx.set_track(tid, t[name + "_x"], t[name + "_y"], float(t[name + "_dl"]))
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="session")
 def mpc():
     """The CUDA context.  Fails (does not skip) when the extension or the GPU is missing:
     -m gpu tests must never pass on a fallback."""

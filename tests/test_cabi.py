@@ -35,6 +35,19 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert sorted(_lib.SIGNATURES) == syms
 
 
+def test_product_library_ships_only_product_kernels():
+    """The shared-memory cross-check kernel (fused_v1.cuh) and the tuning variants live in the separate
+    cross-check build; the product .so must not carry them."""
+    from fsae_mpc_b200 import build
+    build.build()
+    prod = open(build.LIB, "rb").read()
+    xchk = open(build.LIB_XCHECK, "rb").read()
+    assert b"ltvmpc_fused_v1_kernel" not in prod and b"ltvmpc_fused_v1_kernel" in xchk
+    assert prod.count(b"ltvmpc_fused_v2_kernel") > 0
+    # kinematic N = 40 variants (8 / 4 warps, block adds) only in the cross-check build
+    assert b"KinModelELi40ELi2ELi4ELi1" not in prod and b"KinModelELi40ELi2ELi4ELi1" in xchk
+
+
 def test_params_struct_layout_matches_c():
     from fsae_mpc_b200 import _lib
     src = r'''

@@ -70,3 +70,35 @@ def test_dense_qp_bounds_only_and_too_large(mpc):
     assert np.allclose(o["x"], np.clip(-g / 2, -1, 1), atol=1e-12)
     with pytest.raises(fm.FsaeError):
         mpc.qpOASES(np.tile(np.eye(120), (1, 1, 1)), np.zeros((1, 120)), None, -np.ones((1, 120)), np.ones((1, 120)), None, None)
+
+
+def test_dense_qp_flat_variable_on_its_upper_bound(mpc):
+    """A zero-curvature variable with NEGATIVE linear cost starts on its UPPER bound (normal -e_i): x, the
+    multipliers and the working set must come out right, with and without the coupling row active."""
+    from oracle import qp
+    rng = np.random.default_rng(5)
+    B, n, m = 16, 6, 3
+    H = np.zeros((B, n, n)); g = rng.normal(size=(B, n)) * 2
+    A = rng.normal(size=(B, m, n))
+    for b in range(B):
+        G = rng.normal(size=(n - 2, n - 2))
+        H[b, :n - 2, :n - 2] = G @ G.T + 0.5 * np.eye(n - 2)
+    g[:, n - 1] = -np.abs(g[:, n - 1]) - 0.5          # flat, pushed up: starts on ub
+    g[:, n - 2] = np.abs(g[:, n - 2]) + 0.5           # flat, pushed down: starts on lb
+    lb, ub = -np.ones((B, n)), np.ones((B, n))
+    ub[:, n - 1] = rng.uniform(0.5, 2.0, B)
+    A[:, 0, n - 1] = 1.0                              # coupling row that involves the flat variable
+    lbA, ubA = -2.0 * np.ones((B, m)), 2.0 * np.ones((B, m))
+    ubA[::2, 0] = 0.2                                 # every other problem: the row forces it off its bound
+    o = mpc.qpOASES(H, g, A, lb, ub, lbA, ubA)
+    n_off = 0
+    for b in range(B):
+        sol = qp.qpoases(H[b], g[b], A[b], lb[b], ub[b], lbA[b], ubA[b])
+        assert sol.exitflag == 0 and o["exitflag"][b] == 0, b
+        k = qp.kkt_residuals(H[b], g[b], A[b], lb[b], ub[b], lbA[b], ubA[b], o["x"][b], o["lam"][b])
+        assert max(k["primal"], k["stationarity"], k["complementarity"]) < 1e-7, (b, k)
+        assert np.abs(o["x"][b] - sol.x).max() < 1e-7, b
+        assert np.abs(o["lam"][b] - sol.lam).max() < 1e-6 * (1 + np.abs(sol.lam).max()), b
+        assert np.array_equal(o["workingSetB"][b], sol.workingSetB) and np.array_equal(o["workingSetC"][b], sol.workingSetC), b
+        n_off += o["x"][b, n - 1] < ub[b, n - 1] - 1e-9
+    assert (o["workingSetB"][:, n - 1] == 1).any() and n_off >= 2

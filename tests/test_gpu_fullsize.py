@@ -10,7 +10,13 @@ satisfy the KKT conditions of THAT problem:
   dual feasibility     lam >= 0 at lower bounds, <= 0 at upper bounds
 
 A strictly convex QP (in u; exact penalty on the slacks) has ONE point with these properties: the one
-qpOASES returns.  Infeasible problems (exitflag -2) are counted and must be rare."""
+qpOASES returns.  Infeasible problems (exitflag -2) are counted and must be rare.
+
+The certificate's QP data come from the CUDA condense kernel, which shares its model / constraint code
+(models.cuh, cons.cuh) with the fused kernel.  To take that common mode out, every certified batch also
+compares the CUDA condense output of 256 randomly drawn problems OF THAT BATCH with the numpy oracle's
+build_*_qp (itself pinned to the reference's .m files on 112 + 8 reference-executed problems):
+H, f, xA, lb, ub, lbA, ubA to 1e-10 relative."""
 import numpy as np
 import pytest
 
@@ -18,6 +24,32 @@ from conftest import DT
 
 pytestmark = pytest.mark.gpu
 INF = 1e19
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin)
+    assert np.array_equal(np.sign(a[~fin]), np.sign(b[~fin]))
+    return float(np.max(np.abs(a[fin] - b[fin])) / max(1.0, np.max(np.abs(b[fin])))) if fin.any() else 0.0
+
+
+def _condense_matches_oracle(mpc, mid, model, track, x0, xr, xl, ul, t_id, p_id, n_check=256):
+    """CUDA condense vs the oracle on n_check random problems of the batch (perturbed states included)."""
+    from conftest import GoldenTrack
+    from oracle import ltv
+    tr = GoldenTrack(track)
+    build = ltv.build_kinematic_qp if model == "kinematic" else ltv.build_dynamic_qp
+    pick = np.sort(np.random.default_rng(7).choice(x0.shape[0], size=min(n_check, x0.shape[0]), replace=False))
+    q = mpc.condense(mid, x0[pick], xr[pick], DT, xl[pick], ul[pick], track_id=t_id[pick], param_id=p_id[pick])
+    worst = 0.0
+    for j, b in enumerate(pick):
+        o = build(x0[b], xr[b].T, tr.kappa, DT, xl[b].T, ul[b].T)
+        for k in ("H", "f", "xA", "lb", "ub", "lbA", "ubA"):
+            e = _rel(q[k][j], o[k])
+            assert e < 1e-10, (k, int(b), e)
+            worst = max(worst, e)
+    return worst, len(pick)
 
 
 def _certify(mpc, model, track, B, chunk, tid, pid, max_infeasible, N=40):
@@ -50,6 +82,7 @@ def _certify(mpc, model, track, B, chunk, tid, pid, max_infeasible, N=40):
         clear = np.abs(excess) > 1e-7
         assert np.array_equal((~ok)[clear], (excess > 0)[clear]), "exitflag -2 does not coincide with infeasible steering"
     worst = dict(primal=0.0, active=0.0, stat=0.0, dual=0.0)
+    worst["condense_vs_oracle"], worst["condense_checked"] = _condense_matches_oracle(mpc, mid, model, track, x0, xr, xl, ul, t_id, p_id)
     for lo in range(0, B, chunk):
         sl = slice(lo, min(B, lo + chunk))
         keep = ok[sl]

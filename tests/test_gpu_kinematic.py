@@ -144,17 +144,18 @@ def test_closed_loop_lap_matches_oracle_prefix(mpc, fsg):
     assert all(e == 0 for e in h_gpu["exitflag"])
 
 
-def test_kernel_variants_agree(mpc):
-    """v2 (register-tiled product kernel) against v1 (shared-memory variant) on a larger,
-    harder perturbed batch: same exit flags, same solutions."""
+def test_kernel_variants_agree(mpc, mpc_x):
+    """v2 (register-tiled product kernel, from the PRODUCT library) against v1 (shared-memory variant, which
+    only the cross-check build of the library carries) on a larger, harder perturbed batch: same exit flags,
+    same solutions."""
     from fsae_mpc_b200 import workload as wl
     x0, xr, xl, ul = wl.perturbed_batch("kinematic", "fsg2019", 2048, seed=7)
     r2 = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
-    old = mpc.set_kernel_version(1)
+    old = mpc_x.set_kernel_version(1)
     try:
-        r1 = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
+        r1 = mpc_x.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
     finally:
-        mpc.set_kernel_version(old)
+        mpc_x.set_kernel_version(old)
     assert (r2.exitflag == 0).all() and (r1.exitflag == 0).all()
     scale = np.maximum(1.0, np.abs(r1.u_opt).max(axis=1))
     assert (np.abs(r2.u_opt - r1.u_opt).max(axis=1) / scale).max() < 1e-8
@@ -165,18 +166,18 @@ def test_kernel_variants_agree(mpc):
 
 
 @pytest.mark.parametrize("kv", [21, 26, 28, 29])
-def test_warp_count_and_block_size_variants_agree(mpc, kv):
+def test_warp_count_and_block_size_variants_agree(mpc, mpc_x, kv):
     """The dual active-set core is a template over the warp count (tile geometry) and the number of
     constraints taken per search (block size).  Every instantiation must reach the same minimiser and
     the same working set as the product configuration, whatever its pivot order."""
     from fsae_mpc_b200 import workload as wl
     x0, xr, xl, ul = wl.perturbed_batch("kinematic", "fsg2019", 1500, seed=11)
     r2 = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
-    old = mpc.set_kernel_version(kv)
+    old = mpc_x.set_kernel_version(kv)
     try:
-        rv = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
+        rv = mpc_x.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
     finally:
-        mpc.set_kernel_version(old)
+        mpc_x.set_kernel_version(old)
     assert (r2.exitflag == 0).all() and (rv.exitflag == 0).all()
     scale = np.maximum(1.0, np.abs(r2.u_opt).max(axis=1))
     assert (np.abs(rv.u_opt - r2.u_opt).max(axis=1) / scale).max() < 1e-8
