@@ -24,6 +24,8 @@ def load():
     lib.oracle_ltvmpc_kinematic_batch.restype = C.c_int
     lib.oracle_ltvmpc_kinematic_batch.argtypes = [dp, dp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
                                                   dp, dp, dp, dp, dp, dp, ip, dp, dp, ip, C.c_int]
+    lib.oracle_ltvmpc_dynamic_batch.restype = C.c_int
+    lib.oracle_ltvmpc_dynamic_batch.argtypes = lib.oracle_ltvmpc_kinematic_batch.argtypes
     lib.oracle_ltvmpc_kinematic.restype = C.c_int
     lib.oracle_ltvmpc_kinematic.argtypes = [dp, dp, C.c_int, C.c_double, C.c_int, C.c_double,
                                             dp, dp, dp, dp, dp, dp, ip, dp, dp, ip, bp, bp]
@@ -52,13 +54,16 @@ class Baseline:
         self.cores = threads
         self.last = None
 
+    NX, NS, FN = 5, 1, "oracle_ltvmpc_kinematic_batch"
+
     def run(self, x0, x_ref, x_lin, u_lin, dt):
         """Solve all problems of the (C-ABI layout) batch; returns the number solved."""
         B, N = x_ref.shape[0], x_ref.shape[1]
-        x0, x_ref, x_lin, u_lin = (np.ascontiguousarray(a, dtype=np.float64) for a in (x0[:B], x_ref, x_lin, u_lin))
-        out = dict(u_opt=np.empty((B, 2 * N)), x_opt=np.empty((B, 5 * N)), exitflag=np.empty(B, np.int32),
-                   fval=np.empty(B), slack=np.empty((B, 1)), iters=np.empty(B, np.int32))
-        used = self.lib.oracle_ltvmpc_kinematic_batch(
+        assert x0.shape[0] == B == x_lin.shape[0] == u_lin.shape[0], "all four arrays must hold the same problems"
+        x0, x_ref, x_lin, u_lin = (np.ascontiguousarray(a, dtype=np.float64) for a in (x0, x_ref, x_lin, u_lin))
+        out = dict(u_opt=np.empty((B, 2 * N)), x_opt=np.empty((B, self.NX * N)), exitflag=np.empty(B, np.int32),
+                   fval=np.empty(B), slack=np.empty((B, self.NS)), iters=np.empty(B, np.int32))
+        used = getattr(self.lib, self.FN)(
             _dp(self.xs), _dp(self.ys), self.xs.shape[0], self.dl, B, N, float(dt),
             _dp(x0), _dp(x_ref), _dp(x_lin), _dp(u_lin), _dp(out["u_opt"]), _dp(out["x_opt"]),
             out["exitflag"].ctypes.data_as(C.POINTER(C.c_int32)), _dp(out["fval"]), _dp(out["slack"]),
@@ -66,3 +71,8 @@ class Baseline:
         self.cores = used
         self.last = out
         return B
+
+
+class DynamicBaseline(Baseline):
+    """The dynamic (tyre-force) model, ltvmpc_dynamic_curvilinear.m:1 -- oracle_ltvmpc_dynamic_batch."""
+    NX, NS, FN = 7, 4, "oracle_ltvmpc_dynamic_batch"

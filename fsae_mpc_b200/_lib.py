@@ -72,6 +72,16 @@ SIGNATURES = {
                                              C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     "fsae_debug_set_taps": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fsae_probe_fp64_tflops": (C.c_int, [_ctx, C.POINTER(C.c_double)]),
+    "fsae_pool_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]),
+    "fsae_pool_destroy": (C.c_int, [C.c_void_p]),
+    "fsae_pool_size": (C.c_int, [C.c_void_p]),
+    "fsae_pool_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "fsae_pool_last_error": (C.c_char_p, [C.c_void_p]),
+    "fsae_pool_set_track": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, C.c_int, C.c_double]),
+    "fsae_pool_set_params": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Params)]),
+    "fsae_shard_range": (None, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fsae_ltvmpc_host_pool": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, _ip, _ip,
+                                        _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _dp, _ip, _bp, _bp]),
     "fsae_set_host_staging": (C.c_int, [_ctx, C.c_int]),
     "fsae_last_host_path": (C.c_int, [_ctx]),
 }

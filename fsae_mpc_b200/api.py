@@ -339,3 +339,74 @@ class FsaeMpc:
         out = (C.c_uint64 * 3)()
         self._check(self._lib.fsae_debug_counters(self._ctx, out, int(reset)), "fsae_debug_counters")
         return tuple(int(v) for v in out)
+
+
+class FsaePool:
+    """One host thread drives every GPU of the box (fsae_pool_*): the batch is split into contiguous shards
+    (fsae_shard_range == sharding.shard_range) and each shard runs through fsae_ltvmpc_host on its own device,
+    concurrently.  No collective: the problems are independent.  This is the path a single MATLAB process uses
+    (matlab/fsae_mpc_b200_handle.m); bench.py's multi-GPU arm uses one process per GPU instead (torchrun)."""
+
+    def __init__(self, devices=None, lib_path=None):
+        self._lib = _lib.load(lib_path)
+        self._pool = C.c_void_p()
+        if devices is None:
+            rc = self._lib.fsae_pool_create(C.byref(self._pool), None, 0)
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self._lib.fsae_pool_create(C.byref(self._pool), arr, len(devices))
+        if rc != 0:
+            self._pool = None
+            raise FsaeError(f"fsae_pool_create failed with {rc}: sm_100 (B200) GPUs are required; there is no CPU fallback")
+
+    def close(self):
+        if getattr(self, "_pool", None):
+            self._lib.fsae_pool_destroy(self._pool)
+            self._pool = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self._lib.fsae_pool_size(self._pool))
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.fsae_pool_last_error(self._pool)
+            raise FsaeError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def set_track(self, track_id, x_spline, y_spline, dl):
+        xs = np.asfortranarray(x_spline, dtype=np.float64)
+        ys = np.asfortranarray(y_spline, dtype=np.float64)
+        self._check(self._lib.fsae_pool_set_track(self._pool, int(track_id), _dp(xs), _dp(ys), xs.shape[0], float(dl)),
+                    "fsae_pool_set_track")
+
+    def set_params(self, param_id, params):
+        self._check(self._lib.fsae_pool_set_params(self._pool, int(param_id), C.byref(params)), "fsae_pool_set_params")
+
+    def shard_range(self, total, rank):
+        lo, hi = C.c_int64(), C.c_int64()
+        self._lib.fsae_shard_range(int(total), int(rank), len(self), C.byref(lo), C.byref(hi))
+        return int(lo.value), int(hi.value)
+
+    def ltvmpc(self, model, x0, x_ref, dt, x_lin, u_lin, track_id=None, param_id=None):
+        """ltvmpc_*_curvilinear for B problems over all devices of the pool (fsae_ltvmpc_host_pool)."""
+        NX, NU, NS = _DIMS[model]
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        B = x0.shape[0]
+        N = np.asarray(x_ref).shape[1]
+        x0 = _f64(x0, (B, NX)); x_ref = _f64(x_ref, (B, N, NX)); x_lin = _f64(x_lin, (B, N, NX)); u_lin = _f64(u_lin, (B, N, NU))
+        t = None if track_id is None else np.ascontiguousarray(track_id, dtype=np.int32)
+        p = None if param_id is None else np.ascontiguousarray(param_id, dtype=np.int32)
+        nV, nC = NU * N + NS, (6 if model == KINEMATIC else 20) * N
+        r = MpcResult(np.empty((B, NU * N)), np.empty((B, NX * N)), np.empty(B, np.int32), np.empty(B),
+                      np.empty((B, NS)), np.empty(B, np.int32), np.empty((B, nV), np.int8), np.empty((B, nC), np.int8))
+        self._check(self._lib.fsae_ltvmpc_host_pool(
+            self._pool, model, B, N, float(dt), _ip(t), _ip(p), _dp(x0), _dp(x_ref), _dp(x_lin), _dp(u_lin),
+            _dp(r.u_opt), _dp(r.x_opt), _ip(r.exitflag), _dp(r.fval), _dp(r.slack_opt), _ip(r.iters),
+            r.workingSetB.ctypes.data_as(C.POINTER(C.c_int8)), r.workingSetC.ctypes.data_as(C.POINTER(C.c_int8))),
+            "fsae_ltvmpc_host_pool")
+        return r

@@ -567,6 +567,10 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
     int rc = FSAE_ERR_UNSUPPORTED;
     const int kv = ctx->kernel_version;     // 2 = product kernel; others only in the cross-check build
     const int nC = (model == FSAE_MODEL_KINEMATIC) ? 6 * N : 20 * N;
+    // Runtime horizon: the reference takes any N_steps = length(x_ref) (ltvmpc_kinetmatic_curvilinear.m:17).  The
+    // kernels are compiled for horizon capacities 20 / 40 / 80; a problem of N steps runs on the next capacity,
+    // its remaining steps padded inside the kernel (zero state cost, rows disabled).
+    if (N < 1) { ctx->err = "fused step: horizon must be >= 1"; return FSAE_ERR_ARG; }
     if (model == FSAE_MODEL_KINEMATIC) {
 #ifdef FSAE_XCHECK
         if (kv == 1 && (N == 20 || N == 40 || N == 80))
@@ -574,14 +578,14 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
                               N == 80 ? slab_v1_kin80() : 0, NX, NU, NS, nC);
         else
 #endif
-        if (N == 40) rc = launch_fused(ctx, a, st, launch_kin40, kv, 0, NX, NU, NS, nC);
-        else if (N == 20) rc = launch_fused(ctx, a, st, launch_kin20, kv, 0, NX, NU, NS, nC);
-        else if (N == 80) rc = launch_fused(ctx, a, st, launch_kin80, kv, slab_kin80(), NX, NU, NS, nC);
-        else ctx->err = "kinematic fused step: horizon must be 20, 40 or 80";
+        if (N <= 20) rc = launch_fused(ctx, a, st, launch_kin20, kv, 0, NX, NU, NS, nC);
+        else if (N <= 40) rc = launch_fused(ctx, a, st, launch_kin40, kv, 0, NX, NU, NS, nC);
+        else if (N <= 80) rc = launch_fused(ctx, a, st, launch_kin80, kv, slab_kin80(), NX, NU, NS, nC);
+        else ctx->err = "kinematic fused step: horizon must be <= 80 (FSAE_MAX_HORIZON)";
     } else {
-        if (N == 40) rc = launch_fused(ctx, a, st, launch_dyn40, kv, 0, NX, NU, NS, nC);
-        else if (N == 20) rc = launch_fused(ctx, a, st, launch_dyn20, kv, 0, NX, NU, NS, nC);
-        else ctx->err = "dynamic fused step: horizon must be 20 or 40";
+        if (N <= 20) rc = launch_fused(ctx, a, st, launch_dyn20, kv, 0, NX, NU, NS, nC);
+        else if (N <= 40) rc = launch_fused(ctx, a, st, launch_dyn40, kv, 0, NX, NU, NS, nC);
+        else ctx->err = "dynamic fused step: horizon must be <= 40";
     }
     if (rc != FSAE_OK) return rc;
     CK(cudaEventRecord(ctx->ev1, st));
@@ -636,8 +640,27 @@ extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double d
     }
     ctx->last_host_path = staged ? 1 : 0;
     // chunk size: pinned callers 1/8 of a large batch; staged callers 4096 problems (ring slot ~ 16 + 10 MB at N = 40)
-    const int per = staged ? (B >= 8192 ? 4096 : (B + 1) / 2) : (B >= 16384 ? (B + 7) / 8 : B);
-    const int nchunk = (B + per - 1) / per;
+    // staged callers: chunks of ~16 MB of input (4096 problems at N = 40, 8192 at N = 20), at least four per batch
+    int per_staged = (int)(((size_t)16 << 20) / (per_in[0] + per_in[1] + per_in[2] + per_in[3]));
+    per_staged = per_staged < 1024 ? 1024 : (per_staged / 1024) * 1024;
+    if (per_staged > (B + 3) / 4) per_staged = (B + 3) / 4;
+    const int per = staged ? per_staged : (B >= 16384 ? (B + 7) / 8 : B);
+    // chunk boundaries.  Staged callers: the first and last chunks are short (1/4, 1/2 of a chunk), because the
+    // copy-in of the first chunk and the copy-out of the last one cannot overlap any kernel.
+    std::vector<int> cut{0};
+    if (staged && B >= 4 * per) {
+        const int head[2] = {per / 4, per / 2};
+        for (int h : head) cut.push_back(cut.back() + h);
+        const int tail_sz = per / 2 + per / 4;
+        while (B - cut.back() - tail_sz > per) cut.push_back(cut.back() + per);
+        const int rest = B - cut.back();                  // split the remainder: body | 1/2 | 1/4
+        if (rest > tail_sz) cut.push_back(B - tail_sz);
+        cut.push_back(B - per / 4);
+        cut.push_back(B);
+    } else {
+        while (cut.back() < B) cut.push_back(cut.back() + per < B ? cut.back() + per : B);
+    }
+    const int nchunk = (int)cut.size() - 1;
     if (nchunk > 1) {
         // stream2 starts after whatever is already queued on the main stream (ids upload)
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
@@ -660,14 +683,20 @@ extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double d
         lat_out = std::vector<Latch>(nchunk);
     }
     const int T = ctx->copy_threads;
-    auto chunk_n = [&](int c) { const int lo = c * per; return (lo + per <= B) ? per : B - lo; };
+    auto chunk_n = [&](int c) { return cut[c + 1] - cut[c]; };
+    // an array is split over the copy threads in pieces of at least 256 KB (small arrays: one job)
+    auto pieces = [&](size_t bytes) { const size_t k = (bytes + (256u << 10) - 1) / (256u << 10); return (int)(k < 1 ? 1 : (k > (size_t)T ? (size_t)T : k)); };
     // caller -> ring slot, split over the copy threads
     auto post_in = [&](int c) {
-        const int lo = c * per, n = chunk_n(c), slot = c % FSAE_RING;
-        lat_in[c].reset(4 * T);
+        const int lo = cut[c], n = chunk_n(c), slot = c % FSAE_RING;
+        int njobs = 0;
+        for (int i = 0; i < 4; ++i) njobs += pieces(per_in[i] * n);
+        lat_in[c].reset(njobs);
         for (int i = 0; i < 4; ++i) {
-            const size_t tot = per_in[i] * n, piece = ((tot + T - 1) / T + 63) & ~(size_t)63;
-            for (int t = 0; t < T; ++t) {
+            const size_t tot = per_in[i] * n;
+            const int np = pieces(tot);
+            const size_t piece = ((tot + np - 1) / np + 63) & ~(size_t)63;
+            for (int t = 0; t < np; ++t) {
                 const size_t o = (size_t)t * piece, len = o >= tot ? 0 : (o + piece <= tot ? piece : tot - o);
                 CopyJob j;
                 j.dst = ctx->ring_in[slot].p + off_in[i] + o;
@@ -681,14 +710,16 @@ extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double d
     // ring slot -> caller; posted by the main thread once the chunk's D2H copies have completed, so every job in
     // the queue is runnable (a job that waited on an event would block the copy-in jobs queued behind it)
     auto post_out = [&](int c) {
-        const int lo = c * per, n = chunk_n(c), slot = c % FSAE_RING;
+        const int lo = cut[c], n = chunk_n(c), slot = c % FSAE_RING;
         int njobs = 0;
-        for (int i = 0; i < 8; ++i) njobs += dst[i] ? T : 0;
+        for (int i = 0; i < 8; ++i) njobs += dst[i] ? pieces(per_out[i] * n) : 0;
         lat_out[c].reset(njobs);
         for (int i = 0; i < 8; ++i) {
             if (!dst[i]) continue;
-            const size_t tot = per_out[i] * n, piece = ((tot + T - 1) / T + 63) & ~(size_t)63;
-            for (int t = 0; t < T; ++t) {
+            const size_t tot = per_out[i] * n;
+            const int np = pieces(tot);
+            const size_t piece = ((tot + np - 1) / np + 63) & ~(size_t)63;
+            for (int t = 0; t < np; ++t) {
                 const size_t o = (size_t)t * piece, len = o >= tot ? 0 : (o + piece <= tot ? piece : tot - o);
                 CopyJob j;
                 j.dst = dst[i] + per_out[i] * lo + o;
@@ -705,7 +736,7 @@ extern "C" int fsae_ltvmpc_host(fsae_ctx* ctx, int model, int B, int N, double d
     if (staged)
         for (int c = 0; c < AHEAD && c < nchunk; ++c) post_in(c);
     for (int c = 0; c < nchunk; ++c) {
-        const int lo = c * per, n = chunk_n(c), slot = c % FSAE_RING;
+        const int lo = cut[c], n = chunk_n(c), slot = c % FSAE_RING;
         cudaStream_t st = (c & 1) ? ctx->stream2 : ctx->stream;
         if (staged) lat_in[c].wait();
         if (fail_rc == FSAE_OK) {
@@ -771,6 +802,109 @@ extern "C" int fsae_set_host_staging(fsae_ctx* ctx, int mode) {
 }
 // 1 if the most recent fsae_ltvmpc_host call went through the staging ring, 0 if it copied directly
 extern "C" int fsae_last_host_path(const fsae_ctx* ctx) { return ctx ? ctx->last_host_path : -1; }
+
+// ------------------------------------------------------------------ device pool
+// One host thread drives every GPU of the box: the batch is split into contiguous shards (fsae_shard_range,
+// the same rule as fsae_mpc_b200/sharding.py) and each shard runs through fsae_ltvmpc_host on its own context,
+// on a helper thread per device for the duration of the call.  No collective, no peer traffic: the problems
+// are independent.  This is what a single MATLAB process (one MEX handle) uses to reach all 8 GPUs.
+struct fsae_pool {
+    std::vector<fsae_ctx*> ctx;
+    std::string err;
+};
+
+extern "C" void fsae_shard_range(int64_t total, int rank, int world, int64_t* lo, int64_t* hi) {
+    const int64_t base = total / world, rem = total % world;
+    const int64_t l = rank * base + (rank < rem ? rank : rem);
+    if (lo) *lo = l;
+    if (hi) *hi = l + base + (rank < rem ? 1 : 0);
+}
+
+extern "C" int fsae_pool_create(fsae_pool** out, const int* devices, int n_devices) {
+    if (!out) return FSAE_ERR_ARG;
+    *out = nullptr;
+    std::vector<int> devs;
+    if (devices) {
+        if (n_devices < 1) return FSAE_ERR_ARG;
+        devs.assign(devices, devices + n_devices);
+    } else {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) return FSAE_ERR_CUDA;
+        if (n_devices > 0 && n_devices < n) n = n_devices;
+        for (int i = 0; i < n; ++i) devs.push_back(i);
+    }
+    fsae_pool* p = new fsae_pool();
+    for (int d : devs) {
+        fsae_ctx* c = nullptr;
+        const int rc = fsae_create(&c, d);
+        if (rc != FSAE_OK) {
+            for (auto* k : p->ctx) fsae_destroy(k);
+            delete p;
+            return rc;
+        }
+        p->ctx.push_back(c);
+    }
+    *out = p;
+    return FSAE_OK;
+}
+
+extern "C" int fsae_pool_destroy(fsae_pool* p) {
+    if (!p) return FSAE_ERR_ARG;
+    for (auto* c : p->ctx) fsae_destroy(c);
+    delete p;
+    return FSAE_OK;
+}
+extern "C" int fsae_pool_size(const fsae_pool* p) { return p ? (int)p->ctx.size() : 0; }
+extern "C" fsae_ctx* fsae_pool_ctx(fsae_pool* p, int i) { return (p && i >= 0 && i < (int)p->ctx.size()) ? p->ctx[i] : nullptr; }
+extern "C" const char* fsae_pool_last_error(const fsae_pool* p) { return p ? p->err.c_str() : "null pool"; }
+
+extern "C" int fsae_pool_set_track(fsae_pool* p, int track_id, const double* x_spline, const double* y_spline, int n_seg, double dl) {
+    if (!p) return FSAE_ERR_ARG;
+    for (auto* c : p->ctx) {
+        const int rc = fsae_set_track(c, track_id, x_spline, y_spline, n_seg, dl);
+        if (rc != FSAE_OK) { p->err = fsae_last_error(c); return rc; }
+    }
+    return FSAE_OK;
+}
+extern "C" int fsae_pool_set_params(fsae_pool* p, int id, const fsae_params* prm) {
+    if (!p) return FSAE_ERR_ARG;
+    for (auto* c : p->ctx) {
+        const int rc = fsae_set_params(c, id, prm);
+        if (rc != FSAE_OK) { p->err = fsae_last_error(c); return rc; }
+    }
+    return FSAE_OK;
+}
+
+extern "C" int fsae_ltvmpc_host_pool(fsae_pool* p, int model, int B, int N, double dt,
+                                     const int32_t* track_id, const int32_t* param_id,
+                                     const double* x0, const double* x_ref, const double* x_lin, const double* u_lin,
+                                     double* u_opt, double* x_opt, int32_t* exitflag, double* fval,
+                                     double* slack_opt, int32_t* iters, int8_t* workingSetB, int8_t* workingSetC) {
+    int NX, NU, NS;
+    if (!p || p->ctx.empty() || model_dims(model, NX, NU, NS) != FSAE_OK || B < 0 || N < 1) return FSAE_ERR_ARG;
+    if (B == 0) return FSAE_OK;
+    const int W = (int)p->ctx.size();
+    const size_t nU = (size_t)NU * N, nV = nU + NS, nXN = (size_t)NX * N;
+    const size_t nC = (size_t)((model == FSAE_MODEL_KINEMATIC) ? 6 : 20) * N;
+    std::vector<int> rcs(W, FSAE_OK);
+    auto shard = [&](int r) {
+        int64_t lo, hi;
+        fsae_shard_range(B, r, W, &lo, &hi);
+        if (hi <= lo) return;
+        rcs[r] = fsae_ltvmpc_host(p->ctx[r], model, (int)(hi - lo), N, dt, track_id ? track_id + lo : nullptr,
+                                  param_id ? param_id + lo : nullptr, x0 + lo * NX, x_ref + lo * nXN, x_lin + lo * nXN,
+                                  u_lin + lo * nU, u_opt + lo * nU, x_opt + lo * nXN, exitflag + lo, fval + lo,
+                                  slack_opt + lo * NS, iters ? iters + lo : nullptr,
+                                  workingSetB ? workingSetB + lo * nV : nullptr, workingSetC ? workingSetC + lo * nC : nullptr);
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < W; ++r) th.emplace_back(shard, r);
+    shard(0);                                            // the caller's thread drives the first device itself
+    for (auto& t : th) t.join();
+    for (int r = 0; r < W; ++r)
+        if (rcs[r] != FSAE_OK) { p->err = "device " + std::to_string(p->ctx[r]->device) + ": " + fsae_last_error(p->ctx[r]); return rcs[r]; }
+    return FSAE_OK;
+}
 
 // merge exit flags / iteration counts across SQP passes
 __global__ void sqp_merge_kernel(int B, const int32_t* ef_pass, const int32_t* it_pass, int32_t* ef_acc, int32_t* it_acc, int first) {

@@ -38,6 +38,8 @@ struct DenseSm {
 template <int NVMAX>
 struct DenseProb {
     using G = GiCfg<NVMAX, 8>;
+    static constexpr bool REUSE = false;       // no candidate reuse: a row evaluation is a full global-memory dot product
+    __device__ __forceinline__ double eval_code(int) const { return 0.0; }
     DenseSm<NVMAX>& S;
     const double* A;
     const double* lbA;

@@ -118,6 +118,58 @@ struct MpcProb {
     S_t& S;
     const fsae_params& P;
     double dt;
+    // Candidate reuse between full searches (gi_core.cuh, P1), measured on B200: the dynamic model, whose search
+    // evaluates 764 slots, gains 11 % (277 k -> 307 k QP/s at 4 % more iterations); the kinematic model LOSES 16 %
+    // (46.7 -> 59.0 iterations per QP: most-violated pivoting matters more than the cheap search is worth), so it
+    // stays off there.  -DFSAE_REUSE=0/1 overrides for A/B builds.
+#ifdef FSAE_REUSE
+    static constexpr bool REUSE = FSAE_REUSE != 0;
+#else
+    static constexpr bool REUSE = S_t::TWOPHASE;
+#endif
+
+    // Exact value of ONE slot side (code = slot * 2 + upper) at the current x, computed by the whole warp:
+    // negative = violated by that much.  Same arithmetic as search() for that slot (the lanes split the packed
+    // B_bar row by column pairs).
+    __device__ __forceinline__ double eval_code(int code) const {
+        constexpr int NU = D::NU, nU = D::nU, nV = D::nV;
+        const int lane = threadIdx.x & 31;
+        const double* x = S.gi.x;
+        const int slot = code >> 1;
+        const bool upper = code & 1;
+        if (slot < nV) {
+            const double xv = x[slot];
+            const double lb = (slot < nU) ? P.u_lb[slot % NU] : 0.0;
+            const double ub = (slot < nU) ? P.u_ub[slot % NU] : INFINITY;
+            return upper ? ub - xv : xv - lb;
+        }
+        const int rr = slot - nV, r = rr / N, k = rr - r * N;
+        double acc[C::NXS];
+#pragma unroll
+        for (int c = 0; c < C::NXS; ++c) acc[c] = 0.0;
+        const int len = NU * (k + 1);
+        for (int j = 2 * lane; j < len; j += 64) {
+            const double2 xx = *reinterpret_cast<const double2*>(&x[j]);
+#pragma unroll
+            for (int c = 0; c < C::NCR; ++c) {
+                const double2 bb = *reinterpret_cast<const double2*>(&S.Bf[S_t::bfc(c) * D::NPK + D::pk(k, j)]);
+                acc[c] = fma(bb.x, xx.x, fma(bb.y, xx.y, acc[c]));
+            }
+#pragma unroll
+            for (int ci = 0; ci < C::NINT; ++ci) acc[C::NCR + ci] += (C::int_ucol(ci) == 0) ? xx.x : xx.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int c = 0; c < C::NXS; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        }
+#pragma unroll
+        for (int ci = 0; ci < C::NINT; ++ci) acc[C::NCR + ci] *= dt;
+        const double rv = C::row_value(r, acc, S.pc + k * C::NPC, S.cg, x[NU * k]);
+        const int sl = C::row_slack(r);
+        const double sv = sl >= 0 ? x[nU + sl] : 0.0;
+        return upper ? (S.rup[rr] - rv + sv) : (rv + sv - S.rlo[rr]);
+    }
 
     // Threads [0, 4N): 4 lanes per horizon step k compute the constraint-state perturbations
     // xs[., k] = (B_bar_c x)[., k] (packed rows, plus the exact prefix sums of the integrator
@@ -322,8 +374,14 @@ struct MpcProb {
 // The Riccati identity  u'(B_bar' Qbar B_bar + Rbar) u = sum_s |Lambda_s^(1/2) (u_s - K_s x_s)|^2
 // makes J = T^-1 / sqrt 2 (J'HJ = I) the closed-loop response to unit "innovations":
 // u_s = K_s x_s + Lambda_s^(-T/2) v_s.  No dense factorisation of H is needed.
+// Runtime horizon Na <= N (the template's capacity): steps k >= Na are padding -- zero state cost, control cost R
+// (their controls stay exactly 0 and decouple), rows disabled.  State weight of predicted step k (0-based):
+__device__ __forceinline__ double stage_weight(const fsae_params& P, int k, int r, int Na) {
+    return k < Na - 1 ? P.Q[r] : (k == Na - 1 ? P.Q_terminal[r] : 0.0);
+}
+
 template <bool DO_W, bool DO_P, class Model, int N, class S_t>
-__device__ __forceinline__ void horizon_recursions(S_t& S, const fsae_params& P) {
+__device__ __forceinline__ void horizon_recursions(S_t& S, const fsae_params& P, int Na) {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
     constexpr int NX = D::NX, NU = D::NU;
@@ -339,7 +397,7 @@ __device__ __forceinline__ void horizon_recursions(S_t& S, const fsae_params& P)
         double* Sm = BP + NB;               // S = B'P A      [NU][NX]
         double* Kx = Sm + NB;               // K              [NU][NX]
         for (int e = lane; e < NN; e += 32) {
-            const double v = (e / NX == e % NX) ? P.Q_terminal[e / NX] : 0.0;
+            const double v = (e / NX == e % NX) ? stage_weight(P, N - 1, e / NX, Na) : 0.0;
             if (DO_W) Wb[e] = v;
             if (DO_P) Pb[e] = v;
         }
@@ -415,7 +473,7 @@ __device__ __forceinline__ void horizon_recursions(S_t& S, const fsae_params& P)
             for (int e0 = 0; e0 < NN; e0 += 32) {
                 const int e = (e0 + lane < NN) ? e0 + lane : 0;
                 const int i = e / NX, j = e - i * NX;
-                const double qd = (i == j) ? P.Q[i] : 0.0;
+                const double qd = (i == j) ? stage_weight(P, st - 1, i, Na) : 0.0;
                 double aw = qd + ((DO_W && i >= NR_) ? TW[i * NX + j] : 0.0);
                 double ap = qd + ((DO_P && i >= NR_) ? TP[i * NX + j] : 0.0);
                 double sk = 0.0;
@@ -455,7 +513,7 @@ __device__ __forceinline__ void horizon_recursions(S_t& S, const fsae_params& P)
 // symmetric, so columns are read as rows; W A and P A are stored transposed for the same reason), B and the
 // lane's column of A_s in registers.  ~40 shared-memory loads per stage instead of ~66.
 template <class Model, int N, class S_t>
-__device__ __forceinline__ void horizon_recursions_small(S_t& S, const fsae_params& P) {
+__device__ __forceinline__ void horizon_recursions_small(S_t& S, const fsae_params& P, int Na) {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
     constexpr int NX = D::NX, NU = D::NU, NR_ = C::NREAL, NXP = (NX + 1) & ~1, NV2 = NXP / 2;
@@ -480,10 +538,10 @@ __device__ __forceinline__ void horizon_recursions_small(S_t& S, const fsae_para
     double bc[NX], bb0[NX], bb1[NX];
 #pragma unroll
     for (int l = 0; l < NX; ++l) { bc[l] = S.B1[l * NU + c]; bb0[l] = S.B1[l * NU]; bb1[l] = S.B1[l * NU + 1]; }
-    const double r0 = P.R[0], r1 = P.R[1], qd = (i == j) ? P.Q[i] : 0.0;
+    const double r0 = P.R[0], r1 = P.R[1];
     for (int t = lane; t < 2 * NX * NXP; t += 32) {
         const int rr = (t % (NX * NXP)) / NXP, cc = t % NXP;
-        const double v = (rr == cc) ? P.Q_terminal[rr] : 0.0;
+        const double v = (rr == cc) ? stage_weight(P, N - 1, rr, Na) : 0.0;
         Wb[t] = (t < NX * NXP) ? v : 0.0;
         Pb[t] = (t < NX * NXP) ? v : 0.0;
     }
@@ -547,6 +605,7 @@ __device__ __forceinline__ void horizon_recursions_small(S_t& S, const fsae_para
         {
             double tw[NXP], tp[NXP];
             ldrow(TWt, j, tw); ldrow(TPt, j, tp);
+            const double qd = (i == j) ? stage_weight(P, st - 1, i, Na) : 0.0;
             double aw = qd + ((i >= NR_) ? TWt[j * NXP + i] : 0.0);
             double ap = qd + ((i >= NR_) ? TPt[j * NXP + i] : 0.0);
 #pragma unroll
@@ -579,7 +638,9 @@ __device__ __forceinline__ void horizon_recursions_small(S_t& S, const fsae_para
     }
 }
 
-template <class Model, int N, int MINB, int NW_ = 8, int KB_ = 1, int CSR_ = -1>
+// PAD = false: the problem's horizon IS the capacity N (everything about the horizon folds at compile time);
+// PAD = true : runtime horizon a.N < N, the remaining steps are padding.
+template <class Model, int N, int MINB, int NW_ = 8, int KB_ = 1, int CSR_ = -1, bool PAD = false>
 __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchArgs a) {
     using D = Dims<Model, N>;
     using C = Cons<Model>;
@@ -600,6 +661,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     const fsae_params& P = S.prm;      // visible after the barrier that ends the load stage
     const DevTrack tr = a.tracks[a.track_id ? a.track_id[b] : 0];
     const double dt = a.dt;
+    const int Na = PAD ? a.N : N;           // horizon (1 <= Na <= N): steps >= Na are padding
     const int row0 = warp * RPW;            // first row of this warp
     // all real-state rows of B_bar: shared memory, or (LONG) the problem's global slab [B_bar rows | packed H]
     double* const bf_all = LONG ? a.m_scratch + (size_t)b * S_t::SLAB : S.Bf;
@@ -611,12 +673,11 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     // three cp.async.bulk copies that complete on an mbarrier while the other threads clear
     // the working set.  Misaligned caller pointers fall back to plain loads.
     {
-        const double* gxl = a.x_lin + (size_t)b * NX * N;
-        const double* gul = a.u_lin + (size_t)b * NU * N;
-        const double* gxr = a.x_ref + (size_t)b * NX * N;
-        constexpr unsigned BX = NX * N * 8, BU = NU * N * 8;
-        static_assert(BX % 16 == 0 && BU % 16 == 0, "bulk copy sizes must be multiples of 16 bytes");
-        const bool aligned = ((((size_t)gxl) | ((size_t)gul) | ((size_t)gxr)) & 15) == 0;
+        const double* gxl = a.x_lin + (size_t)b * NX * Na;
+        const double* gul = a.u_lin + (size_t)b * NU * Na;
+        const double* gxr = a.x_ref + (size_t)b * NX * Na;
+        const unsigned BX = NX * Na * 8, BU = NU * Na * 8;       // bulk copies need 16-byte sizes and addresses
+        const bool aligned = ((((size_t)gxl) | ((size_t)gul) | ((size_t)gxr) | BX | BU) & 15) == 0;
         if (aligned) {
             if (tid == 0) mbar_init(&S.mbar, 1);
             __syncthreads();
@@ -634,11 +695,19 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
         if (aligned) {
             mbar_wait(&S.mbar, 0);
         } else {
-            for (int i = tid; i < NX * N; i += NT) { S.xl[i] = gxl[i]; S.xr[i] = gxr[i]; }
-            for (int i = tid; i < NU * N; i += NT) S.ul[i] = gul[i];
+            for (int i = tid; i < NX * Na; i += NT) { S.xl[i] = gxl[i]; S.xr[i] = gxr[i]; }
+            for (int i = tid; i < NU * Na; i += NT) S.ul[i] = gul[i];
         }
     }
     __syncthreads();
+    if (PAD && Na < N) {
+        // padding steps repeat the last linearisation point (finite Jacobians; they carry no cost and no rows)
+        for (int i = NX * Na + tid; i < NX * N; i += NT) { S.xl[i] = S.xl[NX * (Na - 1) + i % NX]; S.xr[i] = 0.0; }
+        for (int i = NU * Na + tid; i < NU * N; i += NT) S.ul[i] = S.ul[NU * (Na - 1) + i % NU];
+        for (int t = tid; t < D::NROWS; t += NT)
+            if (t % N >= Na) S.gi.status[nV + t] = 2;            // disabled: never searched, never reported
+        __syncthreads();
+    }
 
     STAGE(0);
     // ---------------------------------------------------------------- linearise + discretise
@@ -691,8 +760,8 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
         else __syncthreads();
     };
     if (warp == GW) {
-        if constexpr (NX * NX <= 32) horizon_recursions_small<Model, N>(S, P);
-        else horizon_recursions<true, true, Model, N>(S, P);
+        if constexpr (NX * NX <= 32) horizon_recursions_small<Model, N>(S, P, Na);
+        else horizon_recursions<true, true, Model, N>(S, P, Na);
     }
     if (warp == NW - 1) {
         if (lane == 0) {
@@ -794,14 +863,14 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
 #pragma unroll
                     for (int ii = 0; ii < C::NREAL; ++ii) {
                         const int r = C::real_state(ii);
-                        const double q = (k == N - 1) ? P.Q_terminal[r] : P.Q[r];
+                        const double q = stage_weight(P, k, r, Na);
                         acc += q * bf_all[ii * D::NPK + D::pk(k, j)] * e[k * NX + r];
                     }
 #pragma unroll
                     for (int ii = 0; ii < C::NINT; ++ii) {
                         if (C::int_ucol(ii) == cj) {
                             const int r = C::int_state(ii);
-                            const double q = (k == N - 1) ? P.Q_terminal[r] : P.Q[r];
+                            const double q = stage_weight(P, k, r, Na);
                             acc += q * dt * e[k * NX + r];
                         }
                     }
@@ -816,7 +885,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             double acc = 0.0;
             for (int i = lane; i < NX * N; i += 32) {
                 const int k = i / NX, r = i - k * NX;
-                const double q = (k == N - 1) ? P.Q_terminal[r] : P.Q[r];
+                const double q = stage_weight(P, k, r, Na);
                 acc += q * e[i] * e[i];
             }
             acc = warp_sum(acc);
@@ -1020,7 +1089,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     Ops::initial_point(Q, m, ybuf, q, nU, nV);             // x_u = -J J' g, slacks at 0
     STAGE(6);
     const MpcProb<Model, N, NW_, KB_, CSR_> prob{S, P, dt};
-    const GiStats st = Ops::solve(prob, Q, m, lam, q, ybuf, nV, P.feas_tol, P.max_iter > 0 ? P.max_iter : 5 * (nV + C::n_ref_rows(N)));
+    const GiStats st = Ops::solve(prob, Q, m, lam, q, ybuf, nV, P.feas_tol, P.max_iter > 0 ? P.max_iter : 5 * (NU * Na + NS + C::n_ref_rows(Na)));
     const int iters = st.iters, exitflag = st.exitflag, n_add = st.n_add, n_drop = st.n_drop, n_refresh = st.n_refresh;
 
     STAGE(7);
@@ -1031,7 +1100,8 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
         if (tid == 0) {
             for (int j = nU; j < nV; ++j) f -= 0.5 * P.flat_eps * Q.x[j] * Q.x[j];
             a.fval[b] = f + S.scal[0];
-            a.exitflag[b] = exitflag;
+            // a non-finite objective means a non-finite iterate: qpOASES's "internal error", never "solved"
+            a.exitflag[b] = (exitflag == GI_EXIT_SOLVED && !isfinite(f)) ? -1 : exitflag;
             if (a.iters) a.iters[b] = iters;
             if (a.counters) {
                 atomicAdd(a.counters + 0, (unsigned long long)n_add);
@@ -1040,11 +1110,11 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             }
         }
     }
-    for (int j = tid; j < nU; j += NT) a.u_opt[(size_t)b * nU + j] = S.gi.x[j];
+    for (int j = tid; j < NU * Na; j += NT) a.u_opt[(size_t)b * NU * Na + j] = S.gi.x[j];
     for (int j = tid; j < NS; j += NT) a.slack_opt[(size_t)b * NS + j] = S.gi.x[nU + j];
     // x_opt = A_bar x0 + B_bar u + d_bar = xf + B_bar u  (ltvmpc_*_curvilinear.m:58)
     {
-        double* gxo = a.x_opt + (size_t)b * NX * N;
+        double* gxo = a.x_opt + (size_t)b * NX * Na;
         constexpr int NRR = C::NREAL * N;
         for (int base = 0; base < NRR; base += NT / 4) {
             const int rid = base + (tid >> 2), part = tid & 3;
@@ -1060,28 +1130,29 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             }
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            if (rid < NRR && part == 0) gxo[k * NX + C::real_state(c)] = S.xf[k * NX + C::real_state(c)] + acc;
+            if (rid < NRR && part == 0 && k < Na) gxo[k * NX + C::real_state(c)] = S.xf[k * NX + C::real_state(c)] + acc;
         }
         for (int t = tid; t < C::NINT * N; t += NT) {
             const int ci = t / N, k = t - ci * N;
             const int uc = C::int_ucol(ci), rs = C::int_state(ci);
             double acc = 0.0;
             for (int i = 0; i <= k; ++i) acc += S.gi.x[NU * i + uc];
-            gxo[k * NX + rs] = S.xf[k * NX + rs] + acc * dt;
+            if (k < Na) gxo[k * NX + rs] = S.xf[k * NX + rs] + acc * dt;
         }
     }
     if (a.wsB) {
-        for (int j = tid; j < nV; j += NT) a.wsB[(size_t)b * nV + j] = S.gi.status[j];
+        const int nUa = NU * Na;               // the caller's variable order: controls of the Na steps, then the slacks
+        for (int j = tid; j < nUa + NS; j += NT) a.wsB[(size_t)b * (nUa + NS) + j] = S.gi.status[j < nUa ? j : nU + (j - nUa)];
     }
     if (a.wsC) {
-        int8_t* w = a.wsC + (size_t)b * C::n_ref_rows(N);
-        for (int j = tid; j < C::n_ref_rows(N); j += NT) w[j] = 0;
+        int8_t* w = a.wsC + (size_t)b * C::n_ref_rows(Na);
+        for (int j = tid; j < C::n_ref_rows(Na); j += NT) w[j] = 0;
         __syncthreads();
         for (int j = tid; j < q; j += NT) {
             const int code = S.gi.act[j], slot = code >> 1, side = (code & 1) ? +1 : -1;
             if (slot >= nV) {
                 const int rr = slot - nV, r = rr / N, k = rr - r * N;
-                w[C::ref_row(r, k, side, N)] = (int8_t)side;
+                w[C::ref_row(r, k, side, Na)] = (int8_t)side;
             }
         }
     }

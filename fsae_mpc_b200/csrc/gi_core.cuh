@@ -436,6 +436,9 @@ struct GiOps {
         GiStats st = {0, GI_EXIT_SOLVED, 0, 0, 0};
         int rbuf = 0, drops_at_refresh = 0;
         bool refresh_failed = false;
+        unsigned long long my_key = DKEY_NONE;      // candidate reuse: this warp's most violated slot of the last full search
+        int my_code = 0x7fffffff;
+        bool have_cand = false;
         PHASE_DECL;
         // drop working-set column l: K1 <- K1 + k r'^T with r' = -K1' H k / k'Hk (k = column l), the freed
         // direction k / sqrt(k'Hk) joins J2 as column q-1, column q-1 of K1 moves into slot l
@@ -508,10 +511,44 @@ struct GiOps {
         };
         while (true) {
             // P1: the KB most violated inactive constraint sides (policy evaluates its slots; one
-            // candidate per thread)
+            // candidate per thread).
+            // Candidate reuse (Prob::REUSE, KB = 1): a full search leaves every warp with its own most violated
+            // slot.  After the global winner has been added, the other warps' candidates are usually still
+            // violated; each warp re-evaluates ITS candidate exactly against the current x (one short
+            // warp-cooperative dot product instead of all slots) and the most violated of them is taken.  Any
+            // violated constraint is a valid pivot of the dual method, and the solve only ends after a FULL search
+            // finds none, so the minimiser (unique) is the same; only the pivot order differs.
             double cviol[KB];
             int ccode[KB];
-            {
+            bool picked = false;
+            if constexpr (Prob::REUSE && KB == 1) {
+                if (have_cand) {
+                    PHASE(0);
+                    double v = 0.0;
+                    if (my_key != DKEY_NONE && S.status[my_code >> 1] == 0) v = prob.eval_code(my_code);
+                    const unsigned long long key = (v < 0.0) ? dkey(v) : DKEY_NONE;
+                    if (lane == 0) { S.red_key[rbuf][warp] = key; S.red_idx[rbuf][warp] = my_code; }
+                    my_key = key;
+                    PHASE(9);
+                    __syncthreads();
+                    unsigned long long ck = DKEY_NONE, km;
+                    int ci = 0x7fffffff;
+                    if (lane < NW) { ck = S.red_key[rbuf][lane]; ci = S.red_idx[rbuf][lane]; }
+                    rbuf ^= 1;
+                    const int wl = warp_argmin_key(ck, km);
+                    ccode[0] = __shfl_sync(0xffffffffu, ci, wl);
+                    cviol[0] = dkey_inv(km);
+                    if (cviol[0] < -tol) {
+                        picked = true;
+                        if (warp == wl) my_key = DKEY_NONE;          // consumed
+                        PHASE_COUNT(13);
+                    } else {
+                        have_cand = false;
+                    }
+                    PHASE(2);
+                }
+            }
+            if (!picked) {
                 double best = 0.0;
                 int best_i = 0x7fffffff;
                 PHASE(0);
@@ -525,6 +562,7 @@ struct GiOps {
                     const int wl = warp_argmin_key(key, km);
                     const int wi = __shfl_sync(0xffffffffu, best_i, wl);
                     if (lane == 0) { S.red_key[rbuf][warp * KB + c] = km; S.red_idx[rbuf][warp * KB + c] = wi; }
+                    if (Prob::REUSE && KB == 1) { my_key = km; my_code = wi; }
                     if (lane == wl) key = DKEY_NONE;
                 }
                 __syncthreads();
@@ -538,8 +576,10 @@ struct GiOps {
                     const int wl = warp_argmin_key(ck, km);
                     ccode[c] = __shfl_sync(0xffffffffu, ci, wl);
                     cviol[c] = dkey_inv(km);
+                    if (Prob::REUSE && KB == 1 && warp == wl) my_key = DKEY_NONE;      // the winner is being added
                     if (lane == wl) ck = DKEY_NONE;
                 }
+                have_cand = Prob::REUSE && KB == 1;
             }
             PHASE(2);
 

@@ -4,8 +4,8 @@ namespace fsae {
 cudaError_t launch_kin20(const BatchArgs& a, cudaStream_t st, int variant) {
 #ifdef FSAE_XCHECK
     switch (variant) {
-        case 21: return launch_v2<KinModel, 20, 2, 8, 1>(a, st);     // 8 warps x 2 CTAs/SM: 3.36M QP/s
-        case 26: return launch_v2<KinModel, 20, 3, 6, 1>(a, st);     // 6 warps x 3: 4.39M
+        case 21: return launch_v2_t<KinModel, 20, 2, 8, 1, -1, false>(a, st);     // 8 warps x 2 CTAs/SM: 3.36M QP/s
+        case 26: return launch_v2_t<KinModel, 20, 3, 6, 1, -1, false>(a, st);     // 6 warps x 3: 4.39M
         default: break;
     }
 #endif

@@ -4,10 +4,10 @@ namespace fsae {
 cudaError_t launch_kin40(const BatchArgs& a, cudaStream_t st, int variant) {
 #ifdef FSAE_XCHECK
     switch (variant) {      // warp count x block size variants (tests, tuning)
-        case 21: return launch_v2<KinModel, 40, 1, 8, 1>(a, st);     // 8 warps (1 CTA/SM: shared memory)
-        case 26: return launch_v2<KinModel, 40, 2, 6, 2>(a, st);     // 6 warps, blocks of 2 constraints per search
-        case 28: return launch_v2<KinModel, 40, 2, 6, 3>(a, st);     // 6 warps, blocks of 3
-        case 29: return launch_v2<KinModel, 40, 2, 4, 1>(a, st);     // 4 warps
+        case 21: return launch_v2_t<KinModel, 40, 1, 8, 1, -1, false>(a, st);     // 8 warps (1 CTA/SM: shared memory)
+        case 26: return launch_v2_t<KinModel, 40, 2, 6, 2, -1, false>(a, st);     // 6 warps, blocks of 2 constraints per search
+        case 28: return launch_v2_t<KinModel, 40, 2, 6, 3, -1, false>(a, st);     // 6 warps, blocks of 3
+        case 29: return launch_v2_t<KinModel, 40, 2, 4, 1, -1, false>(a, st);     // 4 warps
         default: break;
     }
 #endif

@@ -31,6 +31,8 @@ extern "C" {
 #define FSAE_ERR_CUDA -2     /* CUDA runtime error; see fsae_last_error() */
 #define FSAE_ERR_UNSUPPORTED -3
 
+#define FSAE_MAX_HORIZON 80   /* any N_steps in [1, 80] (dynamic model: [1, 40]); N_steps = length(x_ref) as in
+                                 ltvmpc_kinetmatic_curvilinear.m:17 -- not a compile-time choice of the caller */
 #define FSAE_MAX_TRACKS 16
 #define FSAE_MAX_PARAM_SETS 64
 
@@ -174,6 +176,30 @@ int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N_steps, double dt,
 int fsae_set_host_staging(fsae_ctx* ctx, int mode);
 /* 1 if the most recent fsae_ltvmpc_host call used the staging ring, 0 if it copied directly. */
 int fsae_last_host_path(const fsae_ctx* ctx);
+
+/* ---- device pool: ONE host thread (e.g. one MATLAB process) drives all GPUs of the box ---------------
+ * north_star: "the batch ... sharded embarrassingly across the 8 GPUs of one B200 box, with no NCCL on the
+ * solve path".  A pool owns one context per device; fsae_ltvmpc_host_pool splits the batch into contiguous
+ * shards (fsae_shard_range: sizes differ by at most one) and runs each through fsae_ltvmpc_host on its
+ * device, concurrently.  Same arguments and results as fsae_ltvmpc_host.
+ * devices == NULL: the first n_devices visible devices (all of them if n_devices <= 0). */
+typedef struct fsae_pool fsae_pool;
+int fsae_pool_create(fsae_pool** pool, const int* devices, int n_devices);
+int fsae_pool_destroy(fsae_pool* pool);
+int fsae_pool_size(const fsae_pool* pool);
+fsae_ctx* fsae_pool_ctx(fsae_pool* pool, int i);          /* the context of the i-th device (diagnostics) */
+const char* fsae_pool_last_error(const fsae_pool* pool);
+int fsae_pool_set_track(fsae_pool* pool, int track_id, const double* x_spline, const double* y_spline,
+                        int n_seg, double dl);
+int fsae_pool_set_params(fsae_pool* pool, int id, const fsae_params* p);
+void fsae_shard_range(int64_t total, int rank, int world, int64_t* lo, int64_t* hi);
+int fsae_ltvmpc_host_pool(fsae_pool* pool, int model, int B, int N_steps, double dt,
+                          const int32_t* track_id, const int32_t* param_id,
+                          const double* x0, const double* x_ref,
+                          const double* x_lin, const double* u_lin,
+                          double* u_opt, double* x_opt, int32_t* exitflag, double* fval,
+                          double* slack_opt, int32_t* iters,
+                          int8_t* workingSetB, int8_t* workingSetC);
 
 /* ---- sequential QP: n_sqp repeated relinearise + condense + QP passes per problem, each
  * pass linearising at the previous pass's (x_opt, u_opt) -- BASELINE.json configs[3]

@@ -1,5 +1,5 @@
 /* ORACLE (test infrastructure only) -- plain-C restatement of the reference's kinematic
- * LTV-MPC step, used (1) as the CPU baseline bench.py times on the host cores and (2) as a
+ * (and, further down, dynamic) LTV-MPC step, used (1) as the CPU baseline bench.py times on the host cores and (2) as a
  * second checker beside oracle/*.py.  The product never links or calls this file.
  *
  * It follows the reference's DENSE formulation step by step, the way the MATLAB code runs:
@@ -410,6 +410,305 @@ int oracle_ltvmpc_kinematic(const double* xs, const double* ys, int nseg, double
     free(Ad); free(dd); free(Abar); free(Bbar); free(D); free(dbar); free(e); free(H); free(f); free(xA);
     free(lbA); free(ubA); free(lb); free(ub); free(z); free(ws);
     return st;
+}
+
+/* ======================================================================================
+ * Dynamic (tyre-force) model: ltvmpc_dynamic_curvilinear.m:1-62, dense like the reference.
+ *   f_curv_dyn.m:20-63, A_curv_dyn.m:20-106   -> f_dyn(), A_dyn()
+ *   rk4_dynamic_curvilinear.m:25-57           -> lin_rk4_dyn()   (QUIRK: dt/2 in the 4th control sensitivity)
+ *   dynamic_state_constraints.m:10-57 + dynamic_slip_linearise_constraints.m + dynamic_tyre_linearise_constraints.m
+ * ====================================================================================== */
+#define DX 7
+#define DS 4
+#define MASS 280.0
+#define INERTIA 200.0
+#define GRAV 9.81
+#define PB 12.56
+#define PC 1.38
+#define PD 1.60
+#define PE (-0.58)
+
+static double pacejka(double alpha, double Fz) {
+    const double bt = PB * alpha, inner = bt - PE * (bt - atan(bt));
+    return Fz * PD * sin(PC * atan(inner));
+}
+static double pacejka_d(double alpha, double Fz) {
+    const double bt = PB * alpha, inner = bt - PE * (bt - atan(bt));
+    return Fz * PD * cos(PC * atan(inner)) * PC / (1 + inner * inner) * (PB - PE * (PB - PB / (1 + PB * PB * alpha * alpha)));
+}
+typedef struct { double Fcr, Fcr_d, vr, dvr2, xdh, xdhd, vf, dvf2; } dyn_aux_t;
+
+/* f_curv_dyn.m:20-63 */
+static void f_dyn(const double* x, const double* u, const track_t* tr, double* f) {
+    const double n = x[1], mu = x[2], x_d = x[3], y_d = x[4], th = x[5], delta = x[6];
+    const double Fx = u[0] * MASS;
+    const double xdh = x_d + 5 * exp(-x_d / 5);
+    const double k = kappa(tr, x[0]), den = 1 / (1 - n * k);
+    const double af = delta - atan((y_d + LF * th) / xdh), ar = -atan((y_d - LR * th) / xdh);
+    const double Fzf = MASS * GRAV * LR / (LR + LF), Fzr = MASS * GRAV * LF / (LR + LF);
+    const double Fcf = pacejka(af, Fzf), Fcr = pacejka(ar, Fzr);
+    const double sd_ = (x_d * cos(mu) - y_d * sin(mu)) * den;
+    f[0] = sd_;
+    f[1] = x_d * sin(mu) + y_d * cos(mu);
+    f[2] = th - sd_ * k;
+    f[3] = (Fx - Fcf * sin(delta) + MASS * y_d * th) / MASS;
+    f[4] = (Fcr + Fcf * cos(delta) - MASS * x_d * th) / MASS;
+    f[5] = (LF * Fcf * cos(delta) - LR * Fcr) / INERTIA;
+    f[6] = u[1];
+}
+
+/* A_curv_dyn.m:20-106, row-major 7x7 (+ the auxiliaries the constraint linearisations reuse) */
+static void A_dyn(const double* x, const track_t* tr, double* A, dyn_aux_t* ax) {
+    const double m = MASS, I = INERTIA, lr = LR, lf = LF;
+    const double n = x[1], mu = x[2], x_d = x[3], y_d = x[4], th = x[5], delta = x[6];
+    const double xdh = x_d + 5 * exp(-x_d / 5), xdhd = 1 - exp(-x_d / 5);
+    const double af = delta - atan((y_d + lf * th) / xdh), ar = -atan((y_d - lr * th) / xdh);
+    const double Fzf = m * GRAV * lr / (lr + lf), Fzr = m * GRAV * lf / (lr + lf);
+    const double Fcf = pacejka(af, Fzf), Fcr = pacejka(ar, Fzr);
+    const double Fcf_d = pacejka_d(af, Fzf), Fcr_d = pacejka_d(ar, Fzr);
+    const double k = kappa(tr, x[0]), den = 1 / (1 - n * k);
+    const double vf = (y_d + lf * th) / xdh, vr = (y_d - lr * th) / xdh;
+    const double dvf2 = 1 / (1 + vf * vf), dvr2 = 1 / (1 + vr * vr);
+    const double sm = sin(mu), cm = cos(mu), sd = sin(delta), cd = cos(delta);
+    memset(A, 0, 49 * sizeof(double));
+    const double s_n = (x_d * cm - y_d * sm) * den * den * k, s_mu = (-x_d * sm - y_d * cm) * den;
+    const double s_xd = cm * den, s_yd = -sm * den;
+    A[1] = s_n; A[2] = s_mu; A[3] = s_xd; A[4] = s_yd;
+    A[7 + 2] = x_d * cm - y_d * sm; A[7 + 3] = sm; A[7 + 4] = cm;
+    A[14 + 1] = -s_n * k; A[14 + 2] = -s_mu * k; A[14 + 3] = -s_xd * k; A[14 + 4] = -s_yd * k; A[14 + 5] = 1.0;
+    A[21 + 3] = -Fcf_d * dvf2 * vf * sd * xdhd / (m * xdh);
+    A[21 + 4] = (Fcf_d * dvf2 * sd / xdh + m * th) / m;
+    A[21 + 5] = (Fcf_d * dvf2 * lf * sd / xdh + m * y_d) / m;
+    A[21 + 6] = (-Fcf * cd - Fcf_d * sd) / m;
+    A[28 + 3] = (Fcr_d * dvr2 * vr * xdhd / xdh + Fcf_d * dvf2 * vf * cd * xdhd / xdh - m * th) / m;
+    A[28 + 4] = (-Fcr_d * dvr2 / xdh - Fcf_d * dvf2 / xdh * cd) / m;
+    A[28 + 5] = (Fcr_d * dvr2 * lr / xdh - Fcf_d * dvf2 * lf / xdh * cd - m * xdh) / m;
+    A[28 + 6] = (-Fcf * sd + Fcf_d * cd) / m;
+    A[35 + 3] = (lf * Fcf_d * dvf2 * vf * cd * xdhd / xdh - lr * Fcr_d * dvr2 * vr * xdhd / xdh) / I;
+    A[35 + 4] = (-lf * Fcf_d * dvf2 * cd / xdh + lr * Fcr_d * dvr2 / xdh) / I;
+    A[35 + 5] = (-lf * Fcf_d * dvf2 * lf * cd / xdh - lr * Fcr_d * dvr2 * lr / xdh) / I;
+    A[35 + 6] = (-lf * Fcf * sd + lf * Fcf_d * cd) / I;
+    if (ax) { ax->Fcr = Fcr; ax->Fcr_d = Fcr_d; ax->vr = vr; ax->dvr2 = dvr2; ax->xdh = xdh; ax->xdhd = xdhd; ax->vf = vf; ax->dvf2 = dvf2; }
+}
+
+static void mm7(const double* P, const double* Q, double s, double* out /* = P (I + s Q) */) {
+    for (int r = 0; r < DX; ++r)
+        for (int c = 0; c < DX; ++c) {
+            double acc = P[r * DX + c];
+            for (int k = 0; k < DX; ++k) acc += P[r * DX + k] * (Q[k * DX + c] * s);
+            out[r * DX + c] = acc;
+        }
+}
+/* rk4_dynamic_curvilinear.m:25-57; A row-major 7x7, B row-major 7x2 */
+static void lin_rk4_dyn(const double* x, const double* u, const track_t* tr, double dt, double* A, double* B, double* d) {
+    double k1[DX], k2[DX], k3[DX], k4[DX], xt[DX], f[DX];
+    double F1[49], F2[49], F3[49], F4[49], K2[49], K3[49], K4[49];
+    const double B0[DX * NU] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};      /* B_curv_dyn.m: rows 4 and 7 */
+    double U2[DX * NU], U3[DX * NU], U4[DX * NU];
+    f_dyn(x, u, tr, k1);
+    A_dyn(x, tr, F1, 0);
+    for (int i = 0; i < DX; ++i) xt[i] = x[i] + k1[i] * dt / 2;
+    f_dyn(xt, u, tr, k2); A_dyn(xt, tr, F2, 0);
+    for (int i = 0; i < DX; ++i) xt[i] = x[i] + k2[i] * dt / 2;
+    f_dyn(xt, u, tr, k3); A_dyn(xt, tr, F3, 0);
+    for (int i = 0; i < DX; ++i) xt[i] = x[i] + k3[i] * dt;
+    f_dyn(xt, u, tr, k4); A_dyn(xt, tr, F4, 0);
+    mm7(F2, F1, dt / 2, K2);
+    mm7(F3, K2, dt / 2, K3);
+    mm7(F4, K3, dt, K4);
+    for (int r = 0; r < DX; ++r)
+        for (int c = 0; c < NU; ++c) {
+            double a2 = B0[r * NU + c], a3, a4;
+            for (int k = 0; k < DX; ++k) a2 += F2[r * DX + k] * B0[k * NU + c] * dt / 2;
+            U2[r * NU + c] = a2;
+            (void)a3; (void)a4;
+        }
+    for (int r = 0; r < DX; ++r)
+        for (int c = 0; c < NU; ++c) {
+            double a3 = B0[r * NU + c];
+            for (int k = 0; k < DX; ++k) a3 += F3[r * DX + k] * U2[k * NU + c] * dt / 2;
+            U3[r * NU + c] = a3;
+        }
+    for (int r = 0; r < DX; ++r)
+        for (int c = 0; c < NU; ++c) {
+            double a4 = B0[r * NU + c];
+            for (int k = 0; k < DX; ++k) a4 += F4[r * DX + k] * U3[k * NU + c] * dt / 2;     /* QUIRK rk4_*:52 */
+            U4[r * NU + c] = a4;
+        }
+    for (int i = 0; i < 49; ++i) A[i] = (F1[i] + 2 * K2[i] + 2 * K3[i] + K4[i]) / 6;
+    for (int i = 0; i < DX * NU; ++i) B[i] = (B0[i] + 2 * U2[i] + 2 * U3[i] + U4[i]) / 6;
+    for (int r = 0; r < DX; ++r) {
+        f[r] = (k1[r] + 2 * k2[r] + 2 * k3[r] + k4[r]) / 6;
+        double acc = f[r];
+        for (int c = 0; c < DX; ++c) acc -= A[r * DX + c] * x[c];
+        acc -= B[r * NU] * u[0] + B[r * NU + 1] * u[1];
+        d[r] = acc;
+    }
+}
+
+/* One dynamic LTV-MPC step.  x_ref/x_lin [7 x N] column-major, u_lin [2 x N]. */
+int oracle_ltvmpc_dynamic(const double* xs, const double* ys, int nseg, double dl, int N, double dt,
+                          const double* x0, const double* x_ref, const double* x_lin, const double* u_lin,
+                          double* u_opt, double* x_opt, int32_t* exitflag, double* fval, double* slack,
+                          int32_t* iters, int8_t* wsB, int8_t* wsC) {
+    const track_t tr = {xs, ys, nseg, dl};
+    const int nU = NU * N, nV = nU + DS, nXN = DX * N, nC = 20 * N, NP = 12;
+    const double Q[DX] = {5, 250, 2000, 0, 0, 0, 0}, R[NU] = {10, 10}, R_soft[DS] = {1e8, 1e6, 1e6, 1e4};
+    double* Ad = (double*)malloc((size_t)N * 49 * sizeof(double));
+    double* dd = (double*)malloc((size_t)nXN * sizeof(double));
+    double B1[DX * NU];
+    double* Abar = (double*)calloc((size_t)nXN * DX, sizeof(double));
+    double* Bbar = (double*)calloc((size_t)nXN * nV, sizeof(double));
+    double* xf = (double*)calloc(nXN, sizeof(double));
+    double* e = (double*)malloc(nXN * sizeof(double));
+    double* H = (double*)calloc((size_t)nV * nV, sizeof(double));
+    double* f = (double*)calloc(nV, sizeof(double));
+    double* xA = (double*)calloc((size_t)nC * nV, sizeof(double));
+    double* lbA = (double*)malloc(nC * sizeof(double));
+    double* ubA = (double*)malloc(nC * sizeof(double));
+    double* lb = (double*)malloc(nV * sizeof(double));
+    double* ub = (double*)malloc(nV * sizeof(double));
+    double* z = (double*)malloc(nV * sizeof(double));
+    int8_t* ws = (int8_t*)malloc(nV + nC);
+    for (int k = 0; k < N; ++k) {
+        double A[49], B[DX * NU], d[DX];
+        lin_rk4_dyn(x_lin + k * DX, u_lin + k * NU, &tr, dt, A, B, d);
+        for (int r = 0; r < DX; ++r)
+            for (int c = 0; c < DX; ++c) Ad[k * 49 + r * DX + c] = A[r * DX + c] * dt + (r == c);
+        for (int r = 0; r < DX; ++r) dd[k * DX + r] = d[r] * dt;
+        if (k == 0) for (int i = 0; i < DX * NU; ++i) B1[i] = B[i] * dt;
+    }
+    /* A_bar, free response (A_bar x0 + d_bar by the recursion x_f,k = A_k x_f,k-1 + d_k: the same numbers as
+       D * d of sequential_integration.m:38-47 up to round-off) */
+    for (int r = 0; r < DX; ++r) for (int c = 0; c < DX; ++c) Abar[r * DX + c] = Ad[r * DX + c];
+    for (int k = 1; k < N; ++k)
+        for (int r = 0; r < DX; ++r)
+            for (int c = 0; c < DX; ++c) {
+                double s = 0;
+                for (int j = 0; j < DX; ++j) s += Ad[k * 49 + r * DX + j] * Abar[((k - 1) * DX + j) * DX + c];
+                Abar[(k * DX + r) * DX + c] = s;
+            }
+    for (int k = 0; k < N; ++k)
+        for (int r = 0; r < DX; ++r) {
+            double s = dd[k * DX + r];
+            for (int c = 0; c < DX; ++c) s += Ad[k * 49 + r * DX + c] * (k ? xf[(k - 1) * DX + c] : x0[c]);
+            xf[k * DX + r] = s;
+        }
+    for (int i = 0; i < N; ++i) {
+        for (int r = 0; r < DX; ++r) for (int c = 0; c < NU; ++c) Bbar[(size_t)(i * DX + r) * nV + i * NU + c] = B1[r * NU + c];
+        for (int j = i + 1; j < N; ++j)
+            for (int r = 0; r < DX; ++r)
+                for (int c = 0; c < NU; ++c) {
+                    double s = 0;
+                    for (int k = 0; k < DX; ++k) s += Ad[j * 49 + r * DX + k] * Bbar[(size_t)((j - 1) * DX + k) * nV + i * NU + c];
+                    Bbar[(size_t)(j * DX + r) * nV + i * NU + c] = s;
+                }
+    }
+    for (int r = 0; r < nXN; ++r) e[r] = xf[r] - x_ref[r];
+    /* generate_qp.m:23-33 */
+    for (int i = 0; i < nU; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = 0;
+            for (int r = (i / NU) * DX; r < nXN; ++r) {
+                const int k = r / DX, c = r - k * DX;
+                const double qq = (k == N - 1 ? 10 : 1) * Q[c];
+                if (qq != 0) s += qq * Bbar[(size_t)r * nV + i] * Bbar[(size_t)r * nV + j];
+            }
+            if (i == j) s += R[i % NU];
+            H[i * nV + j] = H[j * nV + i] = 2 * s;
+        }
+    double cconst = 0;
+    for (int r = 0; r < nXN; ++r) { const int k = r / DX, c = r - k * DX; cconst += (k == N - 1 ? 10 : 1) * Q[c] * e[r] * e[r]; }
+    for (int j = 0; j < nU; ++j) {
+        double s = 0;
+        for (int r = (j / NU) * DX; r < nXN; ++r) { const int k = r / DX, c = r - k * DX; s += (k == N - 1 ? 10 : 1) * Q[c] * Bbar[(size_t)r * nV + j] * e[r]; }
+        f[j] = 2 * s;
+    }
+    for (int j = 0; j < DS; ++j) f[nU + j] = R_soft[j];
+    /* polygon of dynamic_tyre_linearise_constraints.m:18-23 */
+    double acl[13], all_[13];
+    for (int j = 0; j <= NP; ++j) { const double th = 2 * M_PI * j / NP; acl[j] = 9.163 * sin(th); all_[j] = 10.0 * cos(th); }
+    for (int k = 0; k < N; ++k) {
+        const double* xl = x_lin + k * DX;
+        const double* ul = u_lin + k * NU;
+        const double* xk = xf + k * DX;
+        double Atmp[49];
+        dyn_aux_t ax;
+        A_dyn(xl, &tr, Atmp, &ax);
+        const double cr[3] = {ax.dvr2 * ax.vr * ax.xdhd / ax.xdh, -ax.dvr2 / ax.xdh, ax.dvr2 * LR / ax.xdh};
+        const double cf[3] = {ax.dvf2 * ax.vf * ax.xdhd / ax.xdh, -ax.dvf2 / ax.xdh, -ax.dvf2 * LF / ax.xdh};
+        const double ct[3] = {-ax.Fcr_d * ax.dvr2 * ax.vr * ax.xdhd / ax.xdh / MASS, ax.Fcr_d * ax.dvr2 / ax.xdh / MASS,
+                              -ax.Fcr_d * ax.dvr2 * LR / ax.xdh / MASS};
+        for (int j = 0; j < nU; ++j) {
+            const double bn = Bbar[(size_t)(k * DX + 1) * nV + j], bx = Bbar[(size_t)(k * DX + 3) * nV + j];
+            const double by = Bbar[(size_t)(k * DX + 4) * nV + j], bt = Bbar[(size_t)(k * DX + 5) * nV + j];
+            const double bd = Bbar[(size_t)(k * DX + 6) * nV + j];
+            xA[(size_t)j * nC + k] = bx;
+            xA[(size_t)j * nC + N + k] = bd;
+            xA[(size_t)j * nC + 2 * N + k] = bn;
+            xA[(size_t)j * nC + 3 * N + k] = bn;
+            const double ar_ = cr[0] * bx + cr[1] * by + cr[2] * bt, af_ = cf[0] * bx + cf[1] * by + cf[2] * bt + bd;
+            xA[(size_t)j * nC + 4 * N + 2 * k] = ar_; xA[(size_t)j * nC + 4 * N + 2 * k + 1] = af_;
+            xA[(size_t)j * nC + 6 * N + 2 * k] = ar_; xA[(size_t)j * nC + 6 * N + 2 * k + 1] = af_;
+            const double tb = ct[0] * bx + ct[1] * by + ct[2] * bt;
+            for (int p = 0; p < NP; ++p)
+                xA[(size_t)j * nC + 8 * N + NP * k + p] = (all_[p + 1] - all_[p]) * tb + ((j == NU * k) ? (acl[p + 1] - acl[p]) : 0.0);
+        }
+        xA[(size_t)nU * nC + 2 * N + k] = 1; xA[(size_t)nU * nC + 3 * N + k] = -1;
+        xA[(size_t)(nU + 1) * nC + 4 * N + 2 * k] = 1; xA[(size_t)(nU + 2) * nC + 4 * N + 2 * k + 1] = 1;
+        xA[(size_t)(nU + 1) * nC + 6 * N + 2 * k] = -1; xA[(size_t)(nU + 2) * nC + 6 * N + 2 * k + 1] = -1;
+        for (int p = 0; p < NP; ++p) xA[(size_t)(nU + 3) * nC + 8 * N + NP * k + p] = -1;
+        lbA[k] = 0 - xk[3]; ubA[k] = INFINITY;
+        lbA[N + k] = -0.4 - xk[6]; ubA[N + k] = 0.4 - xk[6];
+        lbA[2 * N + k] = -0.75 - xk[1]; ubA[2 * N + k] = 1e10;
+        lbA[3 * N + k] = -1e10; ubA[3 * N + k] = 0.75 - xk[1];
+        const double d3 = xk[3] - xl[3], d4 = xk[4] - xl[4], d5 = xk[5] - xl[5];
+        const double c_r = -atan(ax.vr) + cr[0] * d3 + cr[1] * d4 + cr[2] * d5;
+        const double c_f = xl[6] - atan(ax.vf) + cf[0] * d3 + cf[1] * d4 + cf[2] * d5 + (xk[6] - xl[6]);
+        lbA[4 * N + 2 * k] = -0.1 - c_r; ubA[4 * N + 2 * k] = INFINITY;
+        lbA[4 * N + 2 * k + 1] = -0.1 - c_f; ubA[4 * N + 2 * k + 1] = INFINITY;
+        lbA[6 * N + 2 * k] = -INFINITY; ubA[6 * N + 2 * k] = 0.1 - c_r;
+        lbA[6 * N + 2 * k + 1] = -INFINITY; ubA[6 * N + 2 * k + 1] = 0.1 - c_f;
+        for (int p = 0; p < NP; ++p) {
+            const double dac = acl[p + 1] - acl[p], dal = all_[p + 1] - all_[p];
+            const double g0 = (ul[0] - all_[p]) * dac - (ax.Fcr / 280 - acl[p]) * dal;
+            const double cc = g0 + dal * (ct[0] * d3 + ct[1] * d4 + ct[2] * d5) - dac * ul[0];
+            lbA[8 * N + NP * k + p] = -INFINITY; ubA[8 * N + NP * k + p] = 0.0 - cc;
+        }
+    }
+    for (int j = 0; j < nU; ++j) { lb[j] = (j % 2) ? -0.4 : -10; ub[j] = (j % 2) ? 0.4 : 10; }
+    for (int j = 0; j < DS; ++j) { lb[nU + j] = 0; ub[nU + j] = INFINITY; }
+    const int flat[DS] = {nU, nU + 1, nU + 2, nU + 3};
+    double fv; int it;
+    const int st = qp_solve(nV, nC, H, f, xA, lb, ub, lbA, ubA, DS, flat, z, &fv, &it, ws);
+    for (int r = 0; r < nXN; ++r) { double s = xf[r]; for (int j = 0; j < nU; ++j) s += Bbar[(size_t)r * nV + j] * z[j]; x_opt[r] = s; }
+    memcpy(u_opt, z, nU * sizeof(double));
+    for (int j = 0; j < DS; ++j) slack[j] = z[nU + j];
+    *fval = fv + cconst;
+    *exitflag = st;
+    if (iters) *iters = it;
+    if (wsB) memcpy(wsB, ws, nV);
+    if (wsC) memcpy(wsC, ws + nV, nC);
+    free(Ad); free(dd); free(Abar); free(Bbar); free(xf); free(e); free(H); free(f); free(xA);
+    free(lbA); free(ubA); free(lb); free(ub); free(z); free(ws);
+    return st;
+}
+
+int oracle_ltvmpc_dynamic_batch(const double* xs, const double* ys, int nseg, double dl, int B, int N, double dt,
+                                const double* x0, const double* x_ref, const double* x_lin, const double* u_lin,
+                                double* u_opt, double* x_opt, int32_t* exitflag, double* fval, double* slack,
+                                int32_t* iters, int nthreads) {
+    int used = 1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    used = omp_get_max_threads();
+#endif
+#pragma omp parallel for schedule(dynamic, 2)
+    for (int b = 0; b < B; ++b)
+        oracle_ltvmpc_dynamic(xs, ys, nseg, dl, N, dt, x0 + (size_t)b * DX, x_ref + (size_t)b * DX * N,
+                              x_lin + (size_t)b * DX * N, u_lin + (size_t)b * NU * N, u_opt + (size_t)b * NU * N,
+                              x_opt + (size_t)b * DX * N, exitflag + b, fval + b, slack + (size_t)b * DS, iters ? iters + b : 0, 0, 0);
+    return used;
 }
 
 /* Batch over B problems in the C-ABI layout (batch trailing), OpenMP over problems. */

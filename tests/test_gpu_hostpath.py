@@ -42,3 +42,26 @@ def test_small_batches_copy_directly(mpc):
     x0, xr, xl, ul = wl.perturbed_batch("kinematic", "fsg2019", 64, seed=3)
     r = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
     assert mpc.last_host_path == 0 and (r.exitflag == 0).all()
+
+
+@pytest.mark.parametrize("n_ctx", [1, 2, 3])
+def test_device_pool_equals_single_context(mpc, n_ctx):
+    """fsae_ltvmpc_host_pool: one host thread, n contexts (here all on device 0 -- the split and the
+    concurrency are what is tested; profiles/ holds the 2- and 8-GPU runs): bit-identical to one context."""
+    import fsae_mpc_b200 as fm
+    from fsae_mpc_b200 import workload as wl
+    from conftest import load_golden
+    B = 5003
+    x0, xr, xl, ul = wl.perturbed_batch("kinematic", "fsg2019", B, seed=5)
+    ref = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
+    pool = fm.FsaePool(devices=[0] * n_ctx)
+    try:
+        assert len(pool) == n_ctx
+        t = load_golden("tracks.npz")
+        pool.set_track(0, t["fsg2019_x"], t["fsg2019_y"], float(t["fsg2019_dl"]))
+        assert sum(h - l for l, h in (pool.shard_range(B, r) for r in range(n_ctx))) == B
+        r = pool.ltvmpc(fm.KINEMATIC, x0, xr, DT, xl, ul)
+    finally:
+        pool.close()
+    for k in ("u_opt", "x_opt", "exitflag", "fval", "slack_opt", "iters", "workingSetB", "workingSetC"):
+        assert np.array_equal(getattr(ref, k), getattr(r, k)), k

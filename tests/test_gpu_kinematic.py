@@ -123,9 +123,9 @@ def test_batch_edge_cases(mpc):
     r1 = mpc.ltvmpc_kinetmatic_curvilinear(g["x0"][:1], xr[:1], DT, xl[:1], ul[:1])
     r7 = mpc.ltvmpc_kinetmatic_curvilinear(g["x0"][:7], xr[:7], DT, xl[:7], ul[:7])
     assert np.array_equal(r1.u_opt[0], r7.u_opt[0])
-    # unsupported horizon is an error, not a silent fallback
+    # a horizon beyond the compiled capacity (FSAE_MAX_HORIZON = 80) is an error, not a silent fallback
     with pytest.raises(fm.FsaeError):
-        mpc.ltvmpc_kinetmatic_curvilinear(g["x0"][:1], xr[:1, :33], DT, xl[:1, :33], ul[:1, :33])
+        mpc.ltvmpc_kinetmatic_curvilinear(g["x0"][:1], np.zeros((1, 81, 5)), DT, np.zeros((1, 81, 5)), np.zeros((1, 81, 2)))
 
 
 def test_closed_loop_lap_matches_oracle_prefix(mpc, fsg):

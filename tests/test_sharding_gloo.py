@@ -26,6 +26,21 @@ def test_shard_range_partitions_exactly():
             assert max(h - l for l, h in sizes) - min(h - l for l, h in sizes) <= 1
 
 
+def test_c_abi_shard_range_equals_python_rule():
+    """fsae_shard_range (the split fsae_ltvmpc_host_pool applies inside ONE process) is the same partition as
+    sharding.shard_range (the split of the one-process-per-GPU path).  Loads the library; no GPU call."""
+    import ctypes as C
+    from fsae_mpc_b200 import _lib
+    from fsae_mpc_b200.sharding import shard_range
+    lib = _lib.load()
+    lo, hi = C.c_int64(), C.c_int64()
+    for total in (0, 1, 7, 65536, 262144, 1000003):
+        for world in (1, 2, 3, 4, 8):
+            for r in range(world):
+                lib.fsae_shard_range(total, r, world, C.byref(lo), C.byref(hi))
+                assert (lo.value, hi.value) == shard_range(total, r, world)
+
+
 def _worker(rank, world, port, out):
     import sys
     sys.path.insert(0, ROOT)
