@@ -443,7 +443,6 @@ extern "C" int fsae_condense_host(fsae_ctx* ctx, int model, int B, int N, double
     int NX, NU, NS;
     if (!ctx || model_dims(model, NX, NU, NS) != FSAE_OK || B < 0 || N <= 0 || N > 80 || !x0 || !x_ref || !x_lin || !u_lin)
         return FSAE_ERR_ARG;
-    if (model == FSAE_MODEL_DYNAMIC && N > 40) { ctx->err = "condense: dynamic model supports N <= 40"; return FSAE_ERR_UNSUPPORTED; }
     if (B == 0) return FSAE_OK;
     int rc = check_ids(ctx, B, track_id, param_id);
     if (rc) return rc;
@@ -478,8 +477,11 @@ extern "C" int fsae_condense_host(fsae_ctx* ctx, int model, int B, int N, double
     a.ub = (lb && ub) ? (double*)ctx->out[6].p : nullptr;
     a.A_bar = (double*)ctx->out[7].p; a.B_bar = (double*)ctx->out[8].p; a.d_bar = (double*)ctx->out[9].p;
     a.cconst = cost_const ? (double*)ctx->out[10].p : nullptr;
-    if (model == FSAE_MODEL_KINEMATIC) condense_kernel<KinModel, 80><<<B, 256, 0, ctx->stream>>>(a);
-    else condense_kernel<DynModel, 40><<<B, 256, 0, ctx->stream>>>(a);
+    const size_t ad_bytes = (size_t)N * NX * NX * sizeof(double);      // the kernel's dynamic shared memory: A_k
+    // static + dynamic shared memory of the dynamic model at long horizons exceeds the 48 KB default: opt in
+    CK(cudaFuncSetAttribute(condense_kernel<DynModel, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 7 * 7 * 8));
+    if (model == FSAE_MODEL_KINEMATIC) condense_kernel<KinModel, 80><<<B, 256, ad_bytes, ctx->stream>>>(a);
+    else condense_kernel<DynModel, 80><<<B, 256, ad_bytes, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     for (int i = 0; i < 11; ++i)
@@ -585,7 +587,8 @@ extern "C" int fsae_ltvmpc_dev(fsae_ctx* ctx, int model, int B, int N, double dt
     } else {
         if (N <= 20) rc = launch_fused(ctx, a, st, launch_dyn20, kv, 0, NX, NU, NS, nC);
         else if (N <= 40) rc = launch_fused(ctx, a, st, launch_dyn40, kv, 0, NX, NU, NS, nC);
-        else ctx->err = "dynamic fused step: horizon must be <= 40";
+        else if (N <= 80) rc = launch_fused(ctx, a, st, launch_dyn80, kv, slab_dyn80(), NX, NU, NS, nC);
+        else ctx->err = "dynamic fused step: horizon must be <= 80 (FSAE_MAX_HORIZON)";
     }
     if (rc != FSAE_OK) return rc;
     CK(cudaEventRecord(ctx->ev1, st));

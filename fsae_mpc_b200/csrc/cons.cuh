@@ -37,6 +37,25 @@ struct Cons<KinModel> {
     static constexpr int NCG = 1;         // per-problem constants (none for this model)
     __device__ static void problem_consts(const fsae_params& p, double* cg) { cg[0] = 0.0; }
     static constexpr int NXS = NCR + NINT;
+    // Every control is integrated exactly by one state (v' = u0, delta' = u1): the solver works in the
+    // integrator coordinates w = T u (w_{2k+c} = dt * sum_{i<=k} u_{2i+c} = the perturbation of v / delta at
+    // step k), where all rows but the n rows have at most three entries (fused_v2.cuh).
+    static constexpr bool WSPACE = true;
+    // w-space normal of row r at step k in  n'x >= b  form (sg = +1 lower side, -1 upper side): entries in
+    // ascending order, 0 = dense row.  nU = index of slack 0.
+    __device__ __forceinline__ static int sparse_row(int r, int k, const double* pc, double sg, int nU,
+                                                     int (&idx)[3], double (&cf)[3]) {
+        switch (r) {
+            case 0: idx[0] = 2 * k; cf[0] = sg; return 1;
+            case 1: idx[0] = 2 * k + 1; cf[0] = sg; return 1;
+            case 2: return 0;
+            default:
+                idx[0] = 2 * k; cf[0] = sg * pc[0];
+                idx[1] = 2 * k + 1; cf[1] = sg * pc[1];
+                idx[2] = nU; cf[2] = 1.0;
+                return 3;
+        }
+    }
     __host__ __device__ static constexpr int real_state(int i) { return i; }        // 0,1,2
     __host__ __device__ static constexpr int cons_real(int i) { return 1; }         // n is real row 1
     __host__ __device__ static constexpr int int_state(int i) { return 3 + i; }     // 3,4
@@ -146,6 +165,8 @@ struct Cons<DynModel> {
     static constexpr int NG0 = 3;         // -atan(vr), delta - atan(vf), Fcr/m
     static constexpr int NCG = 4 * NPOLY; // ac_list, al_list, dac, dal
     static constexpr int NXS = NCR + NINT;
+    static constexpr bool WSPACE = false;      // only delta is an integrator state; the rows that cycle are dense
+    __device__ __forceinline__ static int sparse_row(int, int, const double*, double, int, int (&)[3], double (&)[3]) { return 0; }
     __host__ __device__ static constexpr int real_state(int i) { return i; }
     __host__ __device__ static constexpr int cons_real(int i) { return i == 0 ? 1 : i + 2; }   // 1,3,4,5
     __host__ __device__ static constexpr int int_state(int i) { return 6; }

@@ -43,11 +43,19 @@ struct SmemV2 {
     using C = Cons<Model>;
     using G = CfgV2<Model, N, NW_, KB_, CSR_>;
     static constexpr bool LONG = G::CSS > 0;
-    static constexpr int NBF = LONG ? C::NCR : C::NREAL;                    // B_bar rows in shared memory
+    // BFG: even the B_bar rows the constraints touch do not fit shared memory (dynamic model at horizon 80: 4 x 52 KB);
+    // they are read from the problem's L2-resident slab like the other rows
+    static constexpr bool BFG = LONG && (size_t)C::NCR * D::NPK * sizeof(double) > 65536;
+    static constexpr int NBF = BFG ? 0 : (LONG ? C::NCR : C::NREAL);       // B_bar rows in shared memory
     __host__ __device__ static constexpr int bfc(int c) { return LONG ? c : C::cons_real(c); }   // row of constraint state c
     static constexpr size_t SLAB = LONG ? (size_t)C::NREAL * D::NPK + (size_t)D::nV * D::nV : 0;  // doubles per problem (B_bar rows + full H)
-    alignas(16) double Bf[NBF * D::NPK];        // packed B_bar rows (kept to the end)
-    GiSm<G, D::NSLOT, LONG> gi;                 // x, g, packed H, working set, core scratch
+    static_assert(!BFG || (SLAB % 2 == 0 && D::NPK % 2 == 0), "paired (double2) loads from the slab need 16-byte aligned rows");
+    alignas(16) double Bf[NBF > 0 ? NBF * D::NPK : 2];   // packed B_bar rows (kept to the end)
+    const double* bfg;                          // BFG: this problem's B_bar rows in the slab
+    // packed B_bar row of constraint state c
+    __device__ __forceinline__ const double* crow(int c) const { return BFG ? bfg + C::cons_real(c) * D::NPK : Bf + bfc(c) * D::NPK; }
+    using Gi_t = GiSm<G, D::NSLOT, LONG, C::WSPACE ? D::nU : 0>;
+    Gi_t gi;                                    // x, g, packed H, working set, core scratch
     double B1[D::NX * D::NU];
     double xf[N * D::NX];
     union {
@@ -152,7 +160,7 @@ struct MpcProb {
             const double2 xx = *reinterpret_cast<const double2*>(&x[j]);
 #pragma unroll
             for (int c = 0; c < C::NCR; ++c) {
-                const double2 bb = *reinterpret_cast<const double2*>(&S.Bf[S_t::bfc(c) * D::NPK + D::pk(k, j)]);
+                const double2 bb = *reinterpret_cast<const double2*>(&S.crow(c)[D::pk(k, j)]);
                 acc[c] = fma(bb.x, xx.x, fma(bb.y, xx.y, acc[c]));
             }
 #pragma unroll
@@ -199,7 +207,7 @@ struct MpcProb {
                 const int np = k + 1;                         // double2 pairs of this row
                 const int h = (lanes == 2) ? (np + 1) >> 1 : np;
                 const int p0 = half * h, p1 = (p0 + h < np) ? p0 + h : np;
-                const double* brow = S.Bf + S_t::bfc(c) * D::NPK + D::pk(k, 0);
+                const double* brow = S.crow(c) + D::pk(k, 0);
                 double a1 = 0.0;
                 for (int pp = p0; pp < p1; ++pp) {
                     const double2 xx = *reinterpret_cast<const double2*>(&x[2 * pp]);
@@ -253,6 +261,77 @@ struct MpcProb {
             }
             return;
         }
+        if constexpr (C::WSPACE) {
+            // Integrator coordinates: the v / delta perturbations of step k ARE x[2k], x[2k+1]; only the rows of the
+            // real states need a dot product (packed rows transformed to w-space at setup).  Eight lanes per PAIR of
+            // steps (k, N-1-k): the two packed rows of a pair hold N+1 column pairs together, so every group does
+            // the same work; then each of the eight lanes evaluates one of the pair's 2 x NR rows.
+            static_assert(N % 2 == 0 && C::NR == 4, "step pairs, one row per lane");
+            constexpr int NITER = (N + 1 + 7) / 8;
+            const double idt = S.gi.idt;
+            for (int rt = tid; rt < ROWT; rt += NT) {        // warp-uniform trip count
+                const int gq = rt >> 3, part = rt & 7;
+                const bool valid = gq < N / 2;
+                const int ka = valid ? gq : 0, kb = N - 1 - ka;
+                double accA[C::NCR], accB[C::NCR];
+#pragma unroll
+                for (int c = 0; c < C::NCR; ++c) { accA[c] = 0.0; accB[c] = 0.0; }
+#pragma unroll
+                for (int it = 0; it < NITER; ++it) {
+                    const int p = part + 8 * it;
+                    if (p < N + 1) {
+                        const bool inA = p <= ka;
+                        const int kk = inA ? ka : kb, pp = inA ? p : p - ka - 1;
+                        const double2 xx = *reinterpret_cast<const double2*>(&x[2 * pp]);
+#pragma unroll
+                        for (int c = 0; c < C::NCR; ++c) {
+                            const double2 bb = *reinterpret_cast<const double2*>(&S.crow(c)[D::pk(kk, 2 * pp)]);
+                            const double t = fma(bb.x, xx.x, bb.y * xx.y);
+                            accA[c] += inA ? t : 0.0;
+                            accB[c] += inA ? 0.0 : t;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C::NCR; ++c) {
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        accA[c] += __shfl_xor_sync(0xffffffffu, accA[c], o);
+                        accB[c] += __shfl_xor_sync(0xffffffffu, accB[c], o);
+                    }
+                }
+                if (valid) {
+                    const int k = part < 4 ? ka : kb, r = part & 3;
+                    const int rr = r * N + k, slot = nV + rr;
+                    if (S.gi.status[slot] == 0) {
+                        double acc[C::NXS];
+#pragma unroll
+                        for (int c = 0; c < C::NCR; ++c) acc[c] = part < 4 ? accA[c] : accB[c];
+#pragma unroll
+                        for (int ci = 0; ci < C::NINT; ++ci) acc[C::NCR + ci] = x[NU * k + C::int_ucol(ci)];
+                        const double rv = C::row_value(r, acc, S.pc + k * C::NPC, S.cg, 0.0);
+                        const int sl = C::row_slack(r);
+                        const double sv = sl >= 0 ? x[nU + sl] : 0.0;
+                        const double vlo = rv + sv - S.rlo[rr];
+                        const double vup = S.rup[rr] - rv + sv;
+                        if (vlo < best) { best = vlo; best_i = slot * 2; }
+                        if (vup < best) { best = vup; best_i = slot * 2 + 1; }
+                    }
+                }
+            }
+            // variable bounds: u_i = (w_i - w_{i-2}) / dt for the controls, the slacks as they are
+            for (int slot = (tid + NT - ROWT % NT) % NT; slot < nV; slot += NT) {
+                if (S.gi.status[slot] == 0) {
+                    const double xv = (slot < nU) ? (x[slot] - (slot >= NU ? x[slot - NU] : 0.0)) * idt : x[slot];
+                    const double lb = (slot < nU) ? P.u_lb[slot % NU] : 0.0;
+                    const double ub = (slot < nU) ? P.u_ub[slot % NU] : INFINITY;
+                    const double vlo = xv - lb, vup = ub - xv;
+                    if (vlo < best) { best = vlo; best_i = slot * 2; }
+                    if (vup < best) { best = vup; best_i = slot * 2 + 1; }
+                }
+            }
+            return;
+        }
         for (int rt = tid; rt < ROWT; rt += NT) {            // warp-uniform trip count
             const int k = rt >> 2, part = rt & 3;
             const bool valid = k < N;
@@ -267,7 +346,7 @@ struct MpcProb {
                     const double2 xx = *reinterpret_cast<const double2*>(&x[j]);
 #pragma unroll
                     for (int c = 0; c < C::NCR; ++c) {
-                        const double2 bb = *reinterpret_cast<const double2*>(&S.Bf[S_t::bfc(c) * D::NPK + D::pk(k, j)]);
+                        const double2 bb = *reinterpret_cast<const double2*>(&S.crow(c)[D::pk(k, j)]);
                         acc[c] = fma(bb.x, xx.x, fma(bb.y, xx.y, acc[c]));
                     }
 #pragma unroll
@@ -313,8 +392,34 @@ struct MpcProb {
     // Normal of (slot, side) in  n'x >= b  form.  Everything that depends only on the slot is
     // computed once, warp-uniformly (no divergence); the per-entry part is one shared-memory
     // load and selects.
+    // Normal with at most three entries (ascending), or 0 = dense.  u coordinates: the variable bounds are unit
+    // normals.  Integrator coordinates (C::WSPACE): a control bound is (w_i - w_{i-2}) / dt, rows that touch only
+    // integrator states and a slack have their two or three entries (cons.cuh, sparse_row).
+    __device__ __forceinline__ int sparse_normal(int pslot, int pside, int (&idx)[3], double (&cf)[3]) const {
+        constexpr int NU = D::NU, nU = D::nU, nV = D::nV;
+        const double sg = pside < 0 ? 1.0 : -1.0;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { idx[e] = 0; cf[e] = 0.0; }
+        if (pslot < nV) {
+            if (C::WSPACE && pslot < nU) {
+                const double c = sg * S.gi.idt;
+                if (pslot < NU) { idx[0] = pslot; cf[0] = c; return 1; }
+                idx[0] = pslot - NU; cf[0] = -c;
+                idx[1] = pslot; cf[1] = c;
+                return 2;
+            }
+            idx[0] = pslot; cf[0] = sg;
+            return 1;
+        }
+        if (!C::WSPACE) return 0;
+        const int rr = pslot - nV, r = rr / N, k = rr - r * N;
+        return C::sparse_row(r, k, S.pc + k * C::NPC, sg, nU, idx, cf);
+    }
+
     struct Prep {
         int pslot, k;            // k = horizon step of a row slot, -1 for a variable bound
+        int scnt, sidx[3];       // integrator coordinates: sparse normals (dense fallback of the block variants)
+        double scf[3];
         double sg;
         double creal[C::NCR];    // coefficients of the packed B_bar rows
         double cctl[D::NU];      // dt * (integrator-state coefficients) per control column
@@ -328,6 +433,7 @@ struct MpcProb {
         p.sg = pside < 0 ? 1.0 : -1.0;
         p.k = -1;
         p.slack = -1;
+        p.scnt = C::WSPACE ? sparse_normal(pslot, pside, p.sidx, p.scf) : 0;
 #pragma unroll
         for (int c = 0; c < C::NCR; ++c) p.creal[c] = 0.0;
 #pragma unroll
@@ -341,7 +447,7 @@ struct MpcProb {
 #pragma unroll
             for (int c = 0; c < C::NCR; ++c) p.creal[c] = p.sg * C::row_coef(r, c, pc, S.cg);
 #pragma unroll
-            for (int c = 0; c < C::NINT; ++c) p.cctl[C::int_ucol(c)] += p.sg * dt * C::row_coef(r, C::NCR + c, pc, S.cg);
+            for (int c = 0; c < C::NINT; ++c) p.cctl[C::int_ucol(c)] += p.sg * (C::WSPACE ? 1.0 : dt) * C::row_coef(r, C::NCR + c, pc, S.cg);
 #pragma unroll
             for (int c = 0; c < NU; ++c) p.cu[c] = p.sg * C::row_ucoef(r, c, pc, S.cg);
         }
@@ -349,6 +455,22 @@ struct MpcProb {
     }
     __device__ __forceinline__ double normal_entry(const Prep& p, int i) const {
         constexpr int NU = D::NU, nU = D::nU;
+        if constexpr (C::WSPACE) {
+            if (p.scnt > 0) {                                           // uniform branch
+                double v = 0.0;
+#pragma unroll
+                for (int e = 0; e < 3; ++e) v += (e < p.scnt && i == p.sidx[e]) ? p.scf[e] : 0.0;
+                return v;
+            }
+            // dense row in integrator coordinates: the transformed packed rows, the integrator states' own entries
+            const int step = i / NU, uc = i - step * NU;
+            const bool in = (i < nU) & (step <= p.k);
+            double acc = (step == p.k) ? ((uc == 0) ? p.cctl[0] : p.cctl[NU - 1]) : 0.0;   // (no direct control terms in these models)
+            const int idx = in ? D::pk(p.k, i) : 0;
+#pragma unroll
+            for (int c = 0; c < C::NCR; ++c) acc = fma(p.creal[c], S.crow(c)[idx], acc);
+            return in ? acc : ((i == p.slack) ? 1.0 : 0.0);
+        }
         if (p.k < 0) return (i == p.pslot) ? p.sg : 0.0;               // uniform branch
         const int step = i / NU, uc = i - step * NU;
         const bool in = (i < nU) & (step <= p.k);
@@ -356,14 +478,14 @@ struct MpcProb {
         acc += (step == p.k) ? ((uc == 0) ? p.cu[0] : p.cu[NU - 1]) : 0.0;
         const int idx = in ? D::pk(p.k, i) : 0;
 #pragma unroll
-        for (int c = 0; c < C::NCR; ++c) acc = fma(p.creal[c], S.Bf[S_t::bfc(c) * D::NPK + idx], acc);
+        for (int c = 0; c < C::NCR; ++c) acc = fma(p.creal[c], S.crow(c)[idx], acc);
         return in ? acc : ((i == p.slack) ? 1.0 : 0.0);
     }
 
     __device__ __forceinline__ double norm2(int pslot) const {
         return (pslot < D::nV) ? 1.0 : S.rn2[pslot - D::nV];
     }
-    __device__ __forceinline__ bool is_unit(int pslot) const { return pslot < D::nV; }
+    __device__ __forceinline__ bool is_unit(int pslot) const { return pslot < D::nV && !(C::WSPACE && pslot < D::nU); }
 };
 
 // The two backward recursions over the horizon (s = N-1 .. 0), run by ONE warp each (or both by the same
@@ -665,7 +787,11 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     const int row0 = warp * RPW;            // first row of this warp
     // all real-state rows of B_bar: shared memory, or (LONG) the problem's global slab [B_bar rows | packed H]
     double* const bf_all = LONG ? a.m_scratch + (size_t)b * S_t::SLAB : S.Bf;
-    if (LONG && tid == 0) S.gi.hpg = a.m_scratch + (size_t)b * S_t::SLAB + (size_t)C::NREAL * D::NPK;
+    if (C::WSPACE && tid == 0) S.gi.idt = 1.0 / dt;
+    if (LONG && tid == 0) {
+        S.gi.hpg = a.m_scratch + (size_t)b * S_t::SLAB + (size_t)C::NREAL * D::NPK;
+        S.bfg = bf_all;
+    }
 
     STAGE_DECL;
     // ---------------------------------------------------------------- load (TMA bulk copies)
@@ -810,7 +936,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
                 }
 #pragma unroll
                 for (int ii = 0; ii < C::NREAL; ++ii) bf_all[ii * D::NPK + D::pk(k, t)] = v[C::real_state(ii)];
-                if (LONG) {
+                if (LONG && !S_t::BFG) {
 #pragma unroll
                     for (int c = 0; c < C::NCR; ++c) S.Bf[c * D::NPK + D::pk(k, t)] = v[C::real_state(C::cons_real(c))];
                 }
@@ -838,7 +964,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
                     for (int u = 0; u < NU; ++u) {
                         double bc[C::NCR];
 #pragma unroll
-                        for (int c = 0; c < C::NCR; ++c) bc[c] = S.Bf[S_t::bfc(c) * D::NPK + D::pk(k, j + u)];
+                        for (int c = 0; c < C::NCR; ++c) bc[c] = S.crow(c)[D::pk(k, j + u)];
                         int gi = 0;
 #pragma unroll
                         for (int c = 0; c < C::NCR; ++c) {
@@ -923,7 +1049,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
 #pragma unroll
                     for (int c = 0; c < C::NCR; ++c) {
                         aS += ac[c] * S.csum[(k * C::NCR + c) * NU + u];
-                        aB += ac[c] * S.Bf[S_t::bfc(c) * D::NPK + D::pk(k, NU * k + u)];
+                        aB += ac[c] * S.crow(c)[D::pk(k, NU * k + u)];
                     }
                     const double cu = C::row_ucoef(r, u, pc, S.cg);
                     n2 += bu[u] * (2.0 * aS + (double)(k + 1) * bu[u]) + cu * (2.0 * (aB + bu[u]) + cu);
@@ -995,8 +1121,8 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     // ---------------------------------------------------------------- operator tiles, packed H
     // M = [ e_{nU}, .., e_{nU+NS-1} | J ]: the NS flat (zero-curvature) slack variables start with their
     // lower bound in the working set (q = NS, lam = R_soft: dual feasible), J (J'HJ = I) from the staging.
-    using Ops = GiOps<G, GiSm<G, D::NSLOT, LONG>>;
-    GiSm<G, D::NSLOT, LONG>& Q = S.gi;
+    using Ops = GiOps<G, typename S_t::Gi_t>;
+    typename S_t::Gi_t& Q = S.gi;
     GiTile<G> m;
     double lam[CS];
     int q = NS, ybuf = 0;
@@ -1039,7 +1165,60 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             }
         }
     }
+    // Integrator coordinates (C::WSPACE): the operator the loop works on is T M, rows (k, c) = dt * the prefix sum of
+    // rows (0..k, c) of M.  Every later update is a column operation (M <- M Q, K1 <- K1 - k r'), so it commutes
+    // with T: the loop runs unchanged and produces T z, T x.  Prefix inside the thread's rows, then the carry of
+    // the warps below (published through the ypart scratch).  g becomes T^-T g (difference towards the later step).
+    double g_w = 0.0;
+    if constexpr (C::WSPACE) {
+        static_assert(NT >= nU && NU == 2, "one thread per control for the g stencil; two interleaved channels");
+        if (a.dbg_g) {
+            double* gg = a.dbg_g + (size_t)b * nV;
+            for (int t = tid; t < nV; t += NT) gg[t] = S.gi.g[t];
+        }
+        if (tid < nU) g_w = (S.gi.g[tid] - (tid + NU < nU ? S.gi.g[tid + NU] : 0.0)) * S.gi.idt;
+        double cv[2][CS];
+#pragma unroll
+        for (int s = 0; s < CS; ++s) { cv[0][s] = 0.0; cv[1][s] = 0.0; }
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const int i = row0 + r;
+            if (i < nU) {                               // warp-uniform
+#pragma unroll
+                for (int s = 0; s < CS; ++s) {
+                    if (r >= 2) m(r, s) += m(r >= 2 ? r - 2 : 0, s);
+                    if (i & 1) cv[1][s] = m(r, s); else cv[0][s] = m(r, s);
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < CS; ++s) {
+            S.gi.ypart[0][warp][lane + 32 * s] = cv[0][s];
+            S.gi.ypart[1][warp][lane + 32 * s] = cv[1][s];
+        }
+    }
     __syncthreads();           // staging consumed: the region becomes the packed H
+    if constexpr (C::WSPACE) {
+        if (tid < nU) S.gi.g[tid] = g_w;
+        double c0[CS], c1[CS];
+#pragma unroll
+        for (int s = 0; s < CS; ++s) { c0[s] = 0.0; c1[s] = 0.0; }
+        for (int w = 0; w < warp; ++w) {
+#pragma unroll
+            for (int s = 0; s < CS; ++s) {
+                c0[s] += S.gi.ypart[0][w][lane + 32 * s];
+                c1[s] += S.gi.ypart[1][w][lane + 32 * s];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const int i = row0 + r;
+            if (i < nU) {
+#pragma unroll
+                for (int s = 0; s < CS; ++s) m(r, s) = (m(r, s) + ((i & 1) ? c1[s] : c0[s])) * dt;
+            }
+        }
+    }
     // generate_qp.m:29  H = 2 (B' Qbar B + Rbar), packed lower triangle for the symv's (drops, refresh,
     // objective).  Entry (i, j), i >= j, i the later control at step si:
     //   H_ij = 2 G_si[c_i] . x^(j)_{si+1}  (+ 2 R on the diagonal)
@@ -1075,7 +1254,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             }
         }
     }
-    if (a.dbg_g) {
+    if (!C::WSPACE && a.dbg_g) {
         double* gg = a.dbg_g + (size_t)b * nV;
         for (int t = tid; t < nV; t += NT) gg[t] = S.gi.g[t];
     }
@@ -1085,6 +1264,30 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
         Q.status[nU + tid] = -1;                           // multiplier R_soft (dual feasible start)
     }
     __syncthreads();
+    if constexpr (C::WSPACE) {
+        // packed B_bar rows -> integrator coordinates: (B T^-1)[k][j] = (B[k][j] - B[k][j+2]) / dt, in place, ascending
+        // j (the entry two to the right is still the original one).  One task per (row, channel); tasks of steps k
+        // and N-1-k are paired so that every thread has N+1 entries.
+        static_assert(N % 2 == 0, "step pairs");
+        const double idt = S.gi.idt;
+        constexpr int NROWSETS = C::NREAL + ((LONG && !S_t::BFG) ? C::NCR : 0);
+        for (int task = tid; task < NROWSETS * (N / 2) * NU; task += NT) {
+            const int c = task % NU, t2 = task / NU, g2 = t2 % (N / 2), rs = t2 / (N / 2);
+            double* rowbase = (rs < C::NREAL) ? bf_all + rs * D::NPK : S.Bf + (rs - C::NREAL) * D::NPK;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int k = half ? N - 1 - g2 : g2;
+                double* row = rowbase + D::pk(k, 0);
+                double cur = row[c];
+                for (int j = c; j < NU * (k + 1); j += NU) {
+                    const double nxt = (j + NU < NU * (k + 1)) ? row[j + NU] : 0.0;
+                    row[j] = (cur - nxt) * idt;
+                    cur = nxt;
+                }
+            }
+        }
+        __syncthreads();
+    }
     STAGE(5);
     Ops::initial_point(Q, m, ybuf, q, nU, nV);             // x_u = -J J' g, slacks at 0
     STAGE(6);
@@ -1110,7 +1313,8 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             }
         }
     }
-    for (int j = tid; j < NU * Na; j += NT) a.u_opt[(size_t)b * NU * Na + j] = S.gi.x[j];
+    for (int j = tid; j < NU * Na; j += NT)
+        a.u_opt[(size_t)b * NU * Na + j] = C::WSPACE ? (S.gi.x[j] - (j >= NU ? S.gi.x[j - NU] : 0.0)) * S.gi.idt : S.gi.x[j];
     for (int j = tid; j < NS; j += NT) a.slack_opt[(size_t)b * NS + j] = S.gi.x[nU + j];
     // x_opt = A_bar x0 + B_bar u + d_bar = xf + B_bar u  (ltvmpc_*_curvilinear.m:58)
     {
@@ -1136,8 +1340,12 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             const int ci = t / N, k = t - ci * N;
             const int uc = C::int_ucol(ci), rs = C::int_state(ci);
             double acc = 0.0;
-            for (int i = 0; i <= k; ++i) acc += S.gi.x[NU * i + uc];
-            if (k < Na) gxo[k * NX + rs] = S.xf[k * NX + rs] + acc * dt;
+            if (C::WSPACE) acc = S.gi.x[NU * k + uc];          // the integrator coordinate IS the perturbation of this state
+            else {
+                for (int i = 0; i <= k; ++i) acc += S.gi.x[NU * i + uc];
+                acc *= dt;
+            }
+            if (k < Na) gxo[k * NX + rs] = S.xf[k * NX + rs] + acc;
         }
     }
     if (a.wsB) {

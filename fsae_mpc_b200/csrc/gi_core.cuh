@@ -152,8 +152,13 @@ struct GiTile {
 };
 
 // Shared-memory working set of the core.
-template <class G, int NSLOT, bool HPG = false>
+// WSP > 0: the first WSP variables are held in INTEGRATOR COORDINATES w = T u (two interleaved control channels,
+// w_{2k+c} = dt * sum_{i<=k} u_{2i+c}; see fused_v2.cuh) while the packed H stays in u coordinates: every H v
+// becomes T^-T H T^-1 v, two local difference stencils around the same packed product.
+template <class G, int NSLOT, bool HPG = false, int WSP_ = 0>
 struct GiSm {
+    static constexpr int WSP = WSP_;
+    double idt;                        // 1 / dt (WSP > 0)
     alignas(16) double x[G::RP];
     double g[G::RP];
     double Hp[HPG ? 2 : G::HP];        // packed lower triangle of H (drops, refresh, fval) ...
@@ -261,6 +266,12 @@ struct GiOps {
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row0 = warp * RPW;
         constexpr int SP = G::SP;
         const int CH = (nV + SP - 1) / SP;
+        if constexpr (SM::WSP > 0) {
+            // T^-1 v: back to control increments (difference along each channel, / dt)
+            for (int i = tid; i < nV; i += NT) S.dvec[i] = (i < SM::WSP) ? (v[i] - (i >= 2 ? v[i - 2] : 0.0)) * S.idt : v[i];
+            __syncthreads();
+            v = S.dvec;
+        }
         for (int t = tid; t < SP * nV; t += NT) {
             const int pt = t / nV, i = t - pt * nV;
             const int j0 = pt * CH, j1 = (j0 + CH < nV) ? j0 + CH : nV;
@@ -292,6 +303,17 @@ struct GiOps {
                 double acc = S.wpart[0][i];
 #pragma unroll
                 for (int pt = 1; pt < SP; ++pt) acc += S.wpart[pt][i];
+                if constexpr (SM::WSP > 0) {
+                    if (i < SM::WSP) {             // T^-T: difference towards the later step, / dt
+                        double nxt = 0.0;
+                        if (i + 2 < SM::WSP) {
+                            nxt = S.wpart[0][i + 2];
+#pragma unroll
+                            for (int pt = 1; pt < SP; ++pt) nxt += S.wpart[pt][i + 2];
+                        }
+                        acc = (acc - nxt) * S.idt;
+                    }
+                }
                 S.rowv[i] = acc + (addv ? addv[i] : 0.0);
             }
         }
@@ -639,10 +661,17 @@ struct GiOps {
             for (int c = 0; c < KB; ++c) nleft += (cviol[c] < -tol) ? 1 : 0;
             if (q + nleft > nV) nleft = nV - q > 0 ? nV - q : 1;
 
+            // Sparse normals (KB = 1): a normal with at most three entries (a variable bound, a row that touches only
+            // integrator coordinates and a slack) needs neither its dense vector nor the product M'n -- y is a
+            // combination of at most three ROWS of M, which their owners publish.
+            int sidx[3];
+            double scf[3];
+            int scnt = 0;
+            if constexpr (KB == 1) scnt = prob.sparse_normal(ccode[0] >> 1, (ccode[0] & 1) ? +1 : -1, sidx, scf);
             // P2: this warp's entries of the block's normals; the x the search saw (own rows)
 #pragma unroll
             for (int c = 0; c < KB; ++c) {
-                if (c < nleft) {
+                if (c < nleft && scnt == 0) {
                     const auto prep = prob.normal_prepare(ccode[c] >> 1, (ccode[c] & 1) ? +1 : -1);   // warp-uniform part
                     if (lane < RPW) {
                         const int i = row0 + lane;
@@ -666,7 +695,43 @@ struct GiOps {
                 // publishes its row, nobody multiplies or sums partials.  The spare column carries
                 // n'(x - x_search) for a piggy-backed candidate.
                 double y[CS], dsum = 0.0;
-                if (prob.is_unit(pslot)) {
+                if (KB == 1 && scnt > 0) {
+                    double yp[CS];
+#pragma unroll
+                    for (int s = 0; s < CS; ++s) yp[s] = 0.0;
+                    bool mine = false;
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        const int pr = sidx[e] - row0;             // warp-uniform
+                        if (e < scnt && pr >= 0 && pr < RPW) {
+                            mine = true;
+#pragma unroll
+                            for (int r = 0; r < RPW; ++r)
+                                if (r == pr) {
+#pragma unroll
+                                    for (int s = 0; s < CS; ++s) yp[s] = fma(scf[e], m(r, s), yp[s]);
+                                }
+                        }
+                    }
+                    if (mine) {
+#pragma unroll
+                        for (int s = 0; s < CS; ++s) S.ypart[ybuf][warp][lane + 32 * s] = yp[s];
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int s = 0; s < CS; ++s) y[s] = 0.0;
+                    int lastw = -1;
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {                  // entries ascend: the owners of equal rows are adjacent
+                        const int w = sidx[e < scnt ? e : 0] / RPW;
+                        if (e < scnt && w != lastw) {
+#pragma unroll
+                            for (int s = 0; s < CS; ++s) y[s] += S.ypart[ybuf][w][lane + 32 * s];
+                            lastw = w;
+                        }
+                    }
+                    ybuf ^= 1;
+                } else if (prob.is_unit(pslot)) {
                     const int pr = pslot - row0;               // warp-uniform
                     if (pr >= 0 && pr < RPW) {
 #pragma unroll

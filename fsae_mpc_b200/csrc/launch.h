@@ -14,7 +14,9 @@ cudaError_t launch_kin20(const BatchArgs& a, cudaStream_t st, int variant);
 cudaError_t launch_kin80(const BatchArgs& a, cudaStream_t st, int variant);   // needs a.m_scratch: slab_kin80() doubles per problem
 cudaError_t launch_dyn40(const BatchArgs& a, cudaStream_t st, int variant);
 cudaError_t launch_dyn20(const BatchArgs& a, cudaStream_t st, int variant);
+cudaError_t launch_dyn80(const BatchArgs& a, cudaStream_t st, int variant);   // needs a.m_scratch: slab_dyn80() doubles per problem
 size_t slab_kin80();
+size_t slab_dyn80();
 #ifdef FSAE_XCHECK
 // shared-memory operator kernel (fused_v1.cuh), kinematic only; N = 80 keeps the operator in a global slab
 cudaError_t launch_v1_kin(int N, const BatchArgs& a, cudaStream_t st);

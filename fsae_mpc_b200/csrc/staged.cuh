@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) condense_kernel(CondenseArgs a) {
     constexpr int NX = Model::NX, NU = Model::NU, NS = Model::NS;
     const int N = a.N, b = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
     const int nU = NU * N, nV = nU + NS, nXN = NX * N, nC = C::n_ref_rows(N);
-    __shared__ double Ad[MAXN * NX * NX];
+    extern __shared__ __align__(16) double Ad[];           // [N][NX][NX] (dynamic: N * NX * NX * 8 bytes at launch)
     __shared__ double dd[MAXN * NX];
     __shared__ double B1[NX * NU];
     __shared__ double xf[MAXN * NX];

@@ -31,7 +31,7 @@ extern "C" {
 #define FSAE_ERR_CUDA -2     /* CUDA runtime error; see fsae_last_error() */
 #define FSAE_ERR_UNSUPPORTED -3
 
-#define FSAE_MAX_HORIZON 80   /* any N_steps in [1, 80] (dynamic model: [1, 40]); N_steps = length(x_ref) as in
+#define FSAE_MAX_HORIZON 80   /* any N_steps in [1, 80], both models; N_steps = length(x_ref) as in
                                  ltvmpc_kinetmatic_curvilinear.m:17 -- not a compile-time choice of the caller */
 #define FSAE_MAX_TRACKS 16
 #define FSAE_MAX_PARAM_SETS 64

@@ -61,6 +61,10 @@ def gi_kform(H, g, C, lo, up, W0, eps_flat=1e-8, tol=1e-9, max_iter=500, rule="r
         # steepest-edge like: scale by sqrt(a H^-1 a)
         Y = C @ M
         scale = np.sqrt((Y * Y).sum(1))
+    if rule == "eucl":
+        scale = np.sqrt((C * C).sum(1))
+    if callable(rule):
+        scale = rule(C, M)
     it = 0
     nrefresh = 0
     while True:
