@@ -262,7 +262,7 @@ class FsaeMpc:
     def closed_loop(self, model, plant0, n_sim, N=40, dt=0.05, target_vel=20.0, x_opt0=None, u_opt0=None,
                     track_id=None, param_id=None, history=True):
         """main.m's closed loop for B vehicles (fsae_closed_loop_host).  plant0 (B,7).  The default
-        initial guess is main.m:42-53 (quadratic arc length, linear speed, constant 10 m/s^2).
+        initial guess is main.m:44-55 (quadratic arc length, linear speed, constant 10 m/s^2).
         Returns dict(plant, steps, n_hist (B,n_sim), plant_hist (B,n_sim,7), exit_hist)."""
         NX, NU, NS = _DIMS[model]
         plant0 = np.ascontiguousarray(plant0, dtype=np.float64)

@@ -17,6 +17,7 @@
 // B_bar rows that are exactly dt on the controls up to step k, so they are prefix sums.
 #pragma once
 #include "models.cuh"
+#include "gi_core.cuh"   // SpN
 
 namespace fsae {
 
@@ -40,20 +41,19 @@ struct Cons<KinModel> {
     // Every control is integrated exactly by one state (v' = u0, delta' = u1): the solver works in the
     // integrator coordinates w = T u (w_{2k+c} = dt * sum_{i<=k} u_{2i+c} = the perturbation of v / delta at
     // step k), where all rows but the n rows have at most three entries (fused_v2.cuh).
-    static constexpr bool WSPACE = true;
+    // (The product kernels work in control coordinates: WSPACE is switched on by the model tags KinModelW / KinModelR
+    // below, which the cross-check library instantiates.  Measured on B200, DESIGN.md "Integrator coordinates": the
+    // leaner formulation is 3-7 % SLOWER than control coordinates at horizons 20 and 40.)
+    static constexpr bool WSPACE = false;
+    static constexpr bool USE_RL = false;  // row-lane core (gi_core_rl.cuh); needs WSPACE
     // w-space normal of row r at step k in  n'x >= b  form (sg = +1 lower side, -1 upper side): entries in
     // ascending order, 0 = dense row.  nU = index of slack 0.
-    __device__ __forceinline__ static int sparse_row(int r, int k, const double* pc, double sg, int nU,
-                                                     int (&idx)[3], double (&cf)[3]) {
+    __device__ __forceinline__ static SpN sparse_row(int r, int k, const double* pc, double sg, int nU) {
         switch (r) {
-            case 0: idx[0] = 2 * k; cf[0] = sg; return 1;
-            case 1: idx[0] = 2 * k + 1; cf[0] = sg; return 1;
-            case 2: return 0;
-            default:
-                idx[0] = 2 * k; cf[0] = sg * pc[0];
-                idx[1] = 2 * k + 1; cf[1] = sg * pc[1];
-                idx[2] = nU; cf[2] = 1.0;
-                return 3;
+            case 0: return SpN{1, 2 * k, 0, 0, sg, 0.0, 0.0};
+            case 1: return SpN{1, 2 * k + 1, 0, 0, sg, 0.0, 0.0};
+            case 2: return SpN{0, 0, 0, 0, 0.0, 0.0, 0.0};
+            default: return SpN{3, 2 * k, 2 * k + 1, nU, sg * pc[0], sg * pc[1], 1.0};
         }
     }
     __host__ __device__ static constexpr int real_state(int i) { return i; }        // 0,1,2
@@ -149,6 +149,20 @@ struct Cons<KinModel> {
 };
 
 
+// The kinematic model in integrator coordinates: with the column-lane core (KinModelW) and with the row-lane core
+// (KinModelR).  Same model, same constraints; only the solver's coordinates and operator layout differ.
+struct KinModelW : KinModel {};
+struct KinModelR : KinModel {};
+template <>
+struct Cons<KinModelW> : Cons<KinModel> {
+    static constexpr bool WSPACE = true;
+};
+template <>
+struct Cons<KinModelR> : Cons<KinModel> {
+    static constexpr bool WSPACE = true;
+    static constexpr bool USE_RL = true;
+};
+
 // ---------------------------------------------------------------- dynamic
 // rows per step: 0 x_d (hard), 1 delta (hard), 2 n (soft, slack 0), 3 alpha_r (soft, slack 1),
 //                4 alpha_f (soft, slack 2), 5..16 friction-polygon edges (upper only, slack 3)
@@ -166,7 +180,8 @@ struct Cons<DynModel> {
     static constexpr int NCG = 4 * NPOLY; // ac_list, al_list, dac, dal
     static constexpr int NXS = NCR + NINT;
     static constexpr bool WSPACE = false;      // only delta is an integrator state; the rows that cycle are dense
-    __device__ __forceinline__ static int sparse_row(int, int, const double*, double, int, int (&)[3], double (&)[3]) { return 0; }
+    static constexpr bool USE_RL = false;
+    __device__ __forceinline__ static SpN sparse_row(int, int, const double*, double, int) { return SpN{0, 0, 0, 0, 0.0, 0.0, 0.0}; }
     __host__ __device__ static constexpr int real_state(int i) { return i; }
     __host__ __device__ static constexpr int cons_real(int i) { return i == 0 ? 1 : i + 2; }   // 1,3,4,5
     __host__ __device__ static constexpr int int_state(int i) { return 6; }

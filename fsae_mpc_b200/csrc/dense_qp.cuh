@@ -72,13 +72,9 @@ struct DenseProb {
         return p.sg * A[(size_t)S.perm[i] * nC + (p.pslot - nV)];
     }
     // variable bounds are unit normals: one entry (gi_core.cuh, sparse normals); general rows are dense
-    __device__ __forceinline__ int sparse_normal(int pslot, int pside, int (&idx)[3], double (&cf)[3]) const {
-#pragma unroll
-        for (int e = 0; e < 3; ++e) { idx[e] = 0; cf[e] = 0.0; }
-        if (pslot >= nV) return 0;
-        idx[0] = pslot;
-        cf[0] = pside < 0 ? 1.0 : -1.0;
-        return 1;
+    __device__ __forceinline__ SpN sparse_normal(int pslot, int pside) const {
+        if (pslot >= nV) return spn_none();
+        return SpN{1, pslot, 0, 0, pside < 0 ? 1.0 : -1.0, 0.0, 0.0};
     }
     __device__ __forceinline__ double norm2(int) const { return 1.0; }
     __device__ __forceinline__ bool is_unit(int pslot) const { return pslot < nV; }

@@ -27,6 +27,14 @@
 #pragma once
 #include "batch.cuh"   // BatchArgs, Dims
 #include "gi_core.cuh"
+#include "gi_core_rl.cuh"
+#include <type_traits>
+
+// w-space row search of the kinematic model: 2 = lanes of a step pair split between its two rows (default),
+// 1 = every lane strides through both rows (selects in the loop).  Measured per horizon, see DESIGN.md.
+#ifndef FSAE_SEARCH
+#define FSAE_SEARCH 2
+#endif
 
 namespace fsae {
 
@@ -54,7 +62,10 @@ struct SmemV2 {
     const double* bfg;                          // BFG: this problem's B_bar rows in the slab
     // packed B_bar row of constraint state c
     __device__ __forceinline__ const double* crow(int c) const { return BFG ? bfg + C::cons_real(c) * D::NPK : Bf + bfc(c) * D::NPK; }
-    using Gi_t = GiSm<G, D::NSLOT, LONG, C::WSPACE ? D::nU : 0>;
+    // RL: the row-lane core (gi_core_rl.cuh) for models whose normals are sparse in integrator coordinates
+    static constexpr bool RL = C::USE_RL && C::WSPACE && !LONG && KB_ == 1;
+    using GR = RlCfg<D::nV, NW_>;
+    using Gi_t = std::conditional_t<RL, RlSm<GR, D::NSLOT, D::nU, (D::NS > 0 ? D::nU : -1)>, GiSm<G, D::NSLOT, LONG, C::WSPACE ? D::nU : 0>>;
     Gi_t gi;                                    // x, g, packed H, working set, core scratch
     double B1[D::NX * D::NU];
     double xf[N * D::NX];
@@ -267,17 +278,21 @@ struct MpcProb {
             // steps (k, N-1-k): the two packed rows of a pair hold N+1 column pairs together, so every group does
             // the same work; then each of the eight lanes evaluates one of the pair's 2 x NR rows.
             static_assert(N % 2 == 0 && C::NR == 4, "step pairs, one row per lane");
-            constexpr int NITER = (N + 1 + 7) / 8;
+            // The eight lanes of a group are split between the two rows in proportion to their lengths (nA lanes for
+            // row ka, the others for row kb), each lane striding through ITS row: one accumulator, no selects in the
+            // loop, at most NITER column pairs per lane.
+            constexpr int NITER = (N + 1 + 6) / 7;
             const double idt = S.gi.idt;
             for (int rt = tid; rt < ROWT; rt += NT) {        // warp-uniform trip count
                 const int gq = rt >> 3, part = rt & 7;
                 const bool valid = gq < N / 2;
                 const int ka = valid ? gq : 0, kb = N - 1 - ka;
+#if FSAE_SEARCH == 1
                 double accA[C::NCR], accB[C::NCR];
 #pragma unroll
                 for (int c = 0; c < C::NCR; ++c) { accA[c] = 0.0; accB[c] = 0.0; }
 #pragma unroll
-                for (int it = 0; it < NITER; ++it) {
+                for (int it = 0; it < (N + 1 + 7) / 8; ++it) {       // lane `part` takes every eighth column pair of the two rows
                     const int p = part + 8 * it;
                     if (p < N + 1) {
                         const bool inA = p <= ka;
@@ -300,16 +315,49 @@ struct MpcProb {
                         accB[c] += __shfl_xor_sync(0xffffffffu, accB[c], o);
                     }
                 }
+#else
+                const int nA = (ka + NITER) / NITER;          // ceil((ka + 1) / NITER) lanes for row ka
+                const bool isA = part < nA;
+                const int kk = isA ? ka : kb;
+                const int first = isA ? part : part - nA, stride = isA ? nA : 8 - nA, len = kk + 1;
+                double acc[C::NCR];
+#pragma unroll
+                for (int c = 0; c < C::NCR; ++c) acc[c] = 0.0;
+                const double2* x2 = reinterpret_cast<const double2*>(x);
+#pragma unroll
+                for (int it = 0; it < NITER; ++it) {
+                    const int pp = first + it * stride;
+                    if (pp < len) {
+                        const double2 xx = x2[pp];
+#pragma unroll
+                        for (int c = 0; c < C::NCR; ++c) {
+                            const double2 bb = reinterpret_cast<const double2*>(S.crow(c) + D::pk(kk, 0))[pp];
+                            acc[c] = fma(bb.y, xx.y, fma(bb.x, xx.x, acc[c]));
+                        }
+                    }
+                }
+                double accA[C::NCR], accB[C::NCR];
+#pragma unroll
+                for (int c = 0; c < C::NCR; ++c) {
+                    accA[c] = isA ? acc[c] : 0.0;
+                    accB[c] = isA ? 0.0 : acc[c];
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        accA[c] += __shfl_xor_sync(0xffffffffu, accA[c], o);
+                        accB[c] += __shfl_xor_sync(0xffffffffu, accB[c], o);
+                    }
+                }
+#endif
                 if (valid) {
                     const int k = part < 4 ? ka : kb, r = part & 3;
                     const int rr = r * N + k, slot = nV + rr;
                     if (S.gi.status[slot] == 0) {
-                        double acc[C::NXS];
+                        double av[C::NXS];
 #pragma unroll
-                        for (int c = 0; c < C::NCR; ++c) acc[c] = part < 4 ? accA[c] : accB[c];
+                        for (int c = 0; c < C::NCR; ++c) av[c] = part < 4 ? accA[c] : accB[c];
 #pragma unroll
-                        for (int ci = 0; ci < C::NINT; ++ci) acc[C::NCR + ci] = x[NU * k + C::int_ucol(ci)];
-                        const double rv = C::row_value(r, acc, S.pc + k * C::NPC, S.cg, 0.0);
+                        for (int ci = 0; ci < C::NINT; ++ci) av[C::NCR + ci] = x[NU * k + C::int_ucol(ci)];
+                        const double rv = C::row_value(r, av, S.pc + k * C::NPC, S.cg, 0.0);
                         const int sl = C::row_slack(r);
                         const double sv = sl >= 0 ? x[nU + sl] : 0.0;
                         const double vlo = rv + sv - S.rlo[rr];
@@ -395,31 +443,25 @@ struct MpcProb {
     // Normal with at most three entries (ascending), or 0 = dense.  u coordinates: the variable bounds are unit
     // normals.  Integrator coordinates (C::WSPACE): a control bound is (w_i - w_{i-2}) / dt, rows that touch only
     // integrator states and a slack have their two or three entries (cons.cuh, sparse_row).
-    __device__ __forceinline__ int sparse_normal(int pslot, int pside, int (&idx)[3], double (&cf)[3]) const {
+    __device__ __forceinline__ SpN sparse_normal(int pslot, int pside) const {
         constexpr int NU = D::NU, nU = D::nU, nV = D::nV;
         const double sg = pside < 0 ? 1.0 : -1.0;
-#pragma unroll
-        for (int e = 0; e < 3; ++e) { idx[e] = 0; cf[e] = 0.0; }
         if (pslot < nV) {
             if (C::WSPACE && pslot < nU) {
                 const double c = sg * S.gi.idt;
-                if (pslot < NU) { idx[0] = pslot; cf[0] = c; return 1; }
-                idx[0] = pslot - NU; cf[0] = -c;
-                idx[1] = pslot; cf[1] = c;
-                return 2;
+                if (pslot < NU) return SpN{1, pslot, 0, 0, c, 0.0, 0.0};
+                return SpN{2, pslot - NU, pslot, 0, -c, c, 0.0};
             }
-            idx[0] = pslot; cf[0] = sg;
-            return 1;
+            return SpN{1, pslot, 0, 0, sg, 0.0, 0.0};
         }
-        if (!C::WSPACE) return 0;
+        if (!C::WSPACE) return spn_none();
         const int rr = pslot - nV, r = rr / N, k = rr - r * N;
-        return C::sparse_row(r, k, S.pc + k * C::NPC, sg, nU, idx, cf);
+        return C::sparse_row(r, k, S.pc + k * C::NPC, sg, nU);
     }
 
     struct Prep {
         int pslot, k;            // k = horizon step of a row slot, -1 for a variable bound
-        int scnt, sidx[3];       // integrator coordinates: sparse normals (dense fallback of the block variants)
-        double scf[3];
+        SpN sn;                  // integrator coordinates: sparse normals (dense fallback of the block variants)
         double sg;
         double creal[C::NCR];    // coefficients of the packed B_bar rows
         double cctl[D::NU];      // dt * (integrator-state coefficients) per control column
@@ -433,7 +475,7 @@ struct MpcProb {
         p.sg = pside < 0 ? 1.0 : -1.0;
         p.k = -1;
         p.slack = -1;
-        p.scnt = C::WSPACE ? sparse_normal(pslot, pside, p.sidx, p.scf) : 0;
+        p.sn = C::WSPACE ? sparse_normal(pslot, pside) : spn_none();
 #pragma unroll
         for (int c = 0; c < C::NCR; ++c) p.creal[c] = 0.0;
 #pragma unroll
@@ -456,10 +498,10 @@ struct MpcProb {
     __device__ __forceinline__ double normal_entry(const Prep& p, int i) const {
         constexpr int NU = D::NU, nU = D::nU;
         if constexpr (C::WSPACE) {
-            if (p.scnt > 0) {                                           // uniform branch
+            if (p.sn.cnt > 0) {                                         // uniform branch
                 double v = 0.0;
 #pragma unroll
-                for (int e = 0; e < 3; ++e) v += (e < p.scnt && i == p.sidx[e]) ? p.scf[e] : 0.0;
+                for (int e = 0; e < 3; ++e) v += (e < p.sn.cnt && i == p.sn.idx(e)) ? p.sn.cf(e) : 0.0;
                 return v;
             }
             // dense row in integrator coordinates: the transformed packed rows, the integrator states' own entries
@@ -788,7 +830,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     // all real-state rows of B_bar: shared memory, or (LONG) the problem's global slab [B_bar rows | packed H]
     double* const bf_all = LONG ? a.m_scratch + (size_t)b * S_t::SLAB : S.Bf;
     if (C::WSPACE && tid == 0) S.gi.idt = 1.0 / dt;
-    if (LONG && tid == 0) {
+    if constexpr (LONG) if (tid == 0) {
         S.gi.hpg = a.m_scratch + (size_t)b * S_t::SLAB + (size_t)C::NREAL * D::NPK;
         S.bfg = bf_all;
     }
@@ -816,8 +858,15 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
         }
         for (int i = tid; i < D::NSLOT; i += NT) S.gi.status[i] = 0;
         if (tid == 0) S.prog = N;
-        for (int i = tid; i < KB_ * RP; i += NT) (&S.gi.nvec[0][0])[i] = 0.0;
-        for (int i = tid; i < RP; i += NT) { S.gi.x[i] = 0.0; S.gi.g[i] = 0.0; S.gi.rowv[i] = 0.0; S.gi.zrow[i] = 0.0; S.gi.colk[0][i] = 0.0; S.gi.colk[1][i] = 0.0; }
+        if constexpr (S_t::RL) {
+            for (int i = tid; i < S_t::GR::VL; i += NT) {
+                S.gi.x[i] = 0.0; S.gi.g[i] = 0.0; S.gi.rowv[i] = 0.0; S.gi.nvec[i] = 0.0; S.gi.dvec[i] = 0.0;
+                S.gi.colk[0][i] = 0.0; S.gi.colk[1][i] = 0.0; S.gi.lam[i] = 0.0; S.gi.cs[i] = 1.0;
+            }
+        } else {
+            for (int i = tid; i < KB_ * RP; i += NT) (&S.gi.nvec[0][0])[i] = 0.0;
+            for (int i = tid; i < RP; i += NT) { S.gi.x[i] = 0.0; S.gi.g[i] = 0.0; S.gi.rowv[i] = 0.0; S.gi.zrow[i] = 0.0; S.gi.colk[0][i] = 0.0; S.gi.colk[1][i] = 0.0; }
+        }
         if (aligned) {
             mbar_wait(&S.mbar, 0);
         } else {
@@ -1121,11 +1170,61 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     // ---------------------------------------------------------------- operator tiles, packed H
     // M = [ e_{nU}, .., e_{nU+NS-1} | J ]: the NS flat (zero-curvature) slack variables start with their
     // lower bound in the working set (q = NS, lam = R_soft: dual feasible), J (J'HJ = I) from the staging.
-    using Ops = GiOps<G, typename S_t::Gi_t>;
+    constexpr bool RL = S_t::RL;
+    using GR = typename S_t::GR;
+    using Ops = std::conditional_t<RL, RlOps<GR, typename S_t::Gi_t>, GiOps<G, typename S_t::Gi_t>>;
     typename S_t::Gi_t& Q = S.gi;
-    GiTile<G> m;
+    std::conditional_t<RL, RlTile<GR>, GiTile<G>> m;
     double lam[CS];
     int q = NS, ybuf = 0;
+    double g_w = 0.0;
+    if constexpr (RL) {
+        // Row-lane tiles: thread (warp, lane) holds rows lane + 32 s, columns warp * CPW + c.  Integrator coordinates:
+        // the operator the loop works on is T M (rows (k, c) = dt * the prefix sum of rows (0..k, c) of M); every
+        // later update is a column operation, so it commutes with T and the loop produces T z, T x.  The prefix
+        // runs over the staged rows in shared memory (it commutes with the 2 x 2 column factors applied below).
+        static_assert(NT >= nU && NU == 2, "one thread per control for the g stencil; two interleaved channels");
+        double* Jst = S.gi.hp();
+        auto mval = [&](int i, int jj) -> double {        // entry (i, jj) of [e_slack | J] from the staging
+            if (jj < NS) return (i == nU + jj) ? 1.0 : 0.0;
+            if (jj >= nV || i >= nU) return 0.0;
+            const int j = jj - NS, sj = j / NU, cj = j - sj * NU, si = i / NU, ci = i - si * NU;
+            if (si < sj) return 0.0;
+            const double* jr = Jst + ci * D::NPK + D::pk(si, sj * NU);
+            double v = 0.0;
+#pragma unroll
+            for (int r2 = 0; r2 < NU; ++r2) v = fma(jr[r2], S.Wi[sj * NU * NU + r2 * NU + cj], v);
+            return v;
+        };
+        if (a.dbg_M) {                                   // debug tap: the operator in control coordinates
+            double* gM = a.dbg_M + (size_t)b * nV * nV;
+            for (int t = tid; t < nV * nV; t += NT) gM[t] = mval(t % nV, t / nV);
+        }
+        if (a.dbg_g) {
+            double* gg = a.dbg_g + (size_t)b * nV;
+            for (int t = tid; t < nV; t += NT) gg[t] = S.gi.g[t];
+        }
+        if (tid < nU) g_w = (S.gi.g[tid] - (tid + NU < nU ? S.gi.g[tid + NU] : 0.0)) * S.gi.idt;   // T^-T g
+        if (tid < GR::VL) S.gi.lam[tid] = (tid < NS) ? fabs(S.gi.g[nU + tid]) : 0.0;
+        __syncthreads();
+        for (int task = tid; task < NU * nU; task += NT) {
+            const int ci = task / nU, col = task - ci * nU;
+            double acc = 0.0;
+            for (int si = col / NU; si < N; ++si) {
+                double* pj = Jst + ci * D::NPK + D::pk(si, col);
+                acc += *pj;
+                *pj = acc * dt;
+            }
+        }
+        if (tid < nU) S.gi.g[tid] = g_w;
+        __syncthreads();
+#pragma unroll
+        for (int sl = 0; sl < GR::RS; ++sl) {
+#pragma unroll
+            for (int c = 0; c < GR::CPW; ++c) m(sl, c) = mval(lane + 32 * sl, warp * GR::CPW + c);
+        }
+        __syncthreads();           // staging consumed: the region becomes the packed H
+    } else {
     {
         const double* Jst = S.gi.hp();
         if (LONG) m.attach(S.Msm);
@@ -1165,12 +1264,9 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
             }
         }
     }
-    // Integrator coordinates (C::WSPACE): the operator the loop works on is T M, rows (k, c) = dt * the prefix sum of
-    // rows (0..k, c) of M.  Every later update is a column operation (M <- M Q, K1 <- K1 - k r'), so it commutes
-    // with T: the loop runs unchanged and produces T z, T x.  Prefix inside the thread's rows, then the carry of
-    // the warps below (published through the ypart scratch).  g becomes T^-T g (difference towards the later step).
-    double g_w = 0.0;
-    if constexpr (C::WSPACE) {
+    // Integrator coordinates (C::WSPACE) with the column-lane tiles (long horizons): T M by a prefix inside the
+    // thread's rows, then the carry of the warps below (published through the ypart scratch).  g becomes T^-T g.
+    if constexpr (C::WSPACE && !RL) {
         static_assert(NT >= nU && NU == 2, "one thread per control for the g stencil; two interleaved channels");
         if (a.dbg_g) {
             double* gg = a.dbg_g + (size_t)b * nV;
@@ -1198,7 +1294,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
         }
     }
     __syncthreads();           // staging consumed: the region becomes the packed H
-    if constexpr (C::WSPACE) {
+    if constexpr (C::WSPACE && !RL) {
         if (tid < nU) S.gi.g[tid] = g_w;
         double c0[CS], c1[CS];
 #pragma unroll
@@ -1218,6 +1314,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
                 for (int s = 0; s < CS; ++s) m(r, s) = (m(r, s) + ((i & 1) ? c1[s] : c0[s])) * dt;
             }
         }
+    }
     }
     // generate_qp.m:29  H = 2 (B' Qbar B + Rbar), packed lower triangle for the symv's (drops, refresh,
     // objective).  Entry (i, j), i >= j, i the later control at step si:
@@ -1289,17 +1386,23 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
         __syncthreads();
     }
     STAGE(5);
-    Ops::initial_point(Q, m, ybuf, q, nU, nV);             // x_u = -J J' g, slacks at 0
+    if constexpr (RL) Ops::initial_point(Q, m, q, nU, nV);
+    else Ops::initial_point(Q, m, ybuf, q, nU, nV);        // x_u = -J J' g, slacks at 0
     STAGE(6);
     const MpcProb<Model, N, NW_, KB_, CSR_> prob{S, P, dt};
-    const GiStats st = Ops::solve(prob, Q, m, lam, q, ybuf, nV, P.feas_tol, P.max_iter > 0 ? P.max_iter : 5 * (NU * Na + NS + C::n_ref_rows(Na)));
+    const int iter_cap = P.max_iter > 0 ? P.max_iter : 5 * (NU * Na + NS + C::n_ref_rows(Na));
+    GiStats st;
+    if constexpr (RL) st = Ops::solve(prob, Q, m, q, nV, P.feas_tol, iter_cap);
+    else st = Ops::solve(prob, Q, m, lam, q, ybuf, nV, P.feas_tol, iter_cap);
     const int iters = st.iters, exitflag = st.exitflag, n_add = st.n_add, n_drop = st.n_drop, n_refresh = st.n_refresh;
 
     STAGE(7);
     // ---------------------------------------------------------------- outputs
     // fval = 1/2 x'Hx + g'x + const (ltvmpc_*_curvilinear.m:60); H without the flat_eps entries
     {
-        double f = Ops::objective(Q, nV, nullptr);
+        double f;
+        if constexpr (RL) f = Ops::objective(Q, nV);
+        else f = Ops::objective(Q, nV, nullptr);
         if (tid == 0) {
             for (int j = nU; j < nV; ++j) f -= 0.5 * P.flat_eps * Q.x[j] * Q.x[j];
             a.fval[b] = f + S.scal[0];

@@ -106,6 +106,16 @@ __device__ __forceinline__ double warp_reduce_scatter(double (&v)[RH]) {
     return v[0];
 }
 
+// A constraint normal with at most three entries (rows ascending), cnt = 0: dense.  Scalars, not arrays: the
+// entries must stay in registers (an array that is ever indexed at run time lives in local memory).
+struct SpN {
+    int cnt, i0, i1, i2;
+    double c0, c1, c2;
+    __device__ __forceinline__ int idx(int e) const { return e == 0 ? i0 : (e == 1 ? i1 : i2); }
+    __device__ __forceinline__ double cf(int e) const { return e == 0 ? c0 : (e == 1 ? c1 : c2); }
+};
+__device__ __forceinline__ SpN spn_none() { return SpN{0, 0, 0, 0, 0.0, 0.0, 0.0}; }
+
 // Tile geometry for at most NVMAX variables and NW warps per CTA.
 template <int NVMAX, int NW_ = 8, int KB_ = 1, int CSR_ = -1>
 struct GiCfg {
@@ -664,10 +674,9 @@ struct GiOps {
             // Sparse normals (KB = 1): a normal with at most three entries (a variable bound, a row that touches only
             // integrator coordinates and a slack) needs neither its dense vector nor the product M'n -- y is a
             // combination of at most three ROWS of M, which their owners publish.
-            int sidx[3];
-            double scf[3];
-            int scnt = 0;
-            if constexpr (KB == 1) scnt = prob.sparse_normal(ccode[0] >> 1, (ccode[0] & 1) ? +1 : -1, sidx, scf);
+            SpN spn = spn_none();
+            if constexpr (KB == 1) spn = prob.sparse_normal(ccode[0] >> 1, (ccode[0] & 1) ? +1 : -1);
+            const int scnt = spn.cnt;
             // P2: this warp's entries of the block's normals; the x the search saw (own rows)
 #pragma unroll
             for (int c = 0; c < KB; ++c) {
@@ -702,14 +711,14 @@ struct GiOps {
                     bool mine = false;
 #pragma unroll
                     for (int e = 0; e < 3; ++e) {
-                        const int pr = sidx[e] - row0;             // warp-uniform
+                        const int pr = spn.idx(e) - row0;          // warp-uniform
                         if (e < scnt && pr >= 0 && pr < RPW) {
                             mine = true;
 #pragma unroll
                             for (int r = 0; r < RPW; ++r)
                                 if (r == pr) {
 #pragma unroll
-                                    for (int s = 0; s < CS; ++s) yp[s] = fma(scf[e], m(r, s), yp[s]);
+                                    for (int s = 0; s < CS; ++s) yp[s] = fma(spn.cf(e), m(r, s), yp[s]);
                                 }
                         }
                     }
@@ -723,7 +732,7 @@ struct GiOps {
                     int lastw = -1;
 #pragma unroll
                     for (int e = 0; e < 3; ++e) {                  // entries ascend: the owners of equal rows are adjacent
-                        const int w = sidx[e < scnt ? e : 0] / RPW;
+                        const int w = spn.idx(e) / RPW;
                         if (e < scnt && w != lastw) {
 #pragma unroll
                             for (int s = 0; s < CS; ++s) y[s] += S.ypart[ybuf][w][lane + 32 * s];
@@ -793,7 +802,8 @@ struct GiOps {
                         t1 = dkey_inv(km);
                     }
                     const bool lin_dep = !(d2 > 1e-13 * fmax(1.0, nn));
-                    inv_d2 = __drcp_rn(d2);
+                    const double rs2 = rsqrt(d2);
+                    inv_d2 = rs2 * rs2;             // 2-3 ulp; only scales step lengths and the new column (one special-function chain less)
                     {
                         // Householder scalars of a possible add (rsqrt + reciprocal: ~150 cycles of dependent latency),
                         // issued here so that they overlap the primal step instead of delaying the tile update
@@ -803,7 +813,7 @@ struct GiOps {
                         for (int s = 0; s < CS; ++s)
                             if (s == qs) yq_l = y[s];
                         const double yqv = __shfl_sync(0xffffffffu, yq_l, ql);
-                        const double delta = d2 * rsqrt(d2);
+                        const double delta = d2 * rs2;
                         sgd = (yqv >= 0.0) ? delta : -delta;
                         beta = __drcp_rn(d2 + fabs(yqv) * delta);
                     }

@@ -8,6 +8,8 @@ cudaError_t launch_kin40(const BatchArgs& a, cudaStream_t st, int variant) {
         case 26: return launch_v2_t<KinModel, 40, 2, 6, 2, -1, false>(a, st);     // 6 warps, blocks of 2 constraints per search
         case 28: return launch_v2_t<KinModel, 40, 2, 6, 3, -1, false>(a, st);     // 6 warps, blocks of 3
         case 29: return launch_v2_t<KinModel, 40, 2, 4, 1, -1, false>(a, st);     // 4 warps
+        case 31: return launch_v2_t<KinModelW, 40, 2, 6, 1, -1, false>(a, st);    // integrator coordinates, column-lane core
+        case 32: return launch_v2_t<KinModelR, 40, 2, 6, 1, -1, false>(a, st);    // integrator coordinates, row-lane core
         default: break;
     }
 #endif

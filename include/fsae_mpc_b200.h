@@ -36,7 +36,7 @@ extern "C" {
 #define FSAE_MAX_TRACKS 16
 #define FSAE_MAX_PARAM_SETS 64
 
-/* Model selectors (main.m:28 MODEL = "KINEMATIC" | "DYNAMIC"). */
+/* Model selectors (main.m:26 MODEL = "KINEMATIC" | "DYNAMIC"). */
 #define FSAE_MODEL_KINEMATIC 0
 #define FSAE_MODEL_DYNAMIC 1
 
@@ -204,7 +204,7 @@ int fsae_ltvmpc_host_pool(fsae_pool* pool, int model, int B, int N_steps, double
 /* ---- sequential QP: n_sqp repeated relinearise + condense + QP passes per problem, each
  * pass linearising at the previous pass's (x_opt, u_opt) -- BASELINE.json configs[3]
  * ("mpc/nonlinear SQP: repeated relinearise+QP iterations per step").  It is exactly what
- * main.m:113-118 does across consecutive time steps (x_lin/u_lin = previous x_opt/u_opt),
+ * main.m:118-127 does across consecutive time steps (x_lin/u_lin = previous x_opt/u_opt),
  * iterated on a frozen x0/x_ref.  n_sqp = 1 is fsae_ltvmpc_host.  Outputs are those of the
  * last pass; exitflag is the first non-zero flag met (0 if every pass solved). */
 int fsae_ltvmpc_sqp_host(fsae_ctx* ctx, int model, int B, int N_steps, double dt, int n_sqp,
@@ -214,15 +214,15 @@ int fsae_ltvmpc_sqp_host(fsae_ctx* ctx, int model, int B, int N_steps, double dt
                          double* u_opt, double* x_opt, int32_t* exitflag, double* fval,
                          double* slack_opt, int32_t* iters);
 
-/* ---- batch driver: main.m's closed loop (main.m:87-170) for B vehicles ----------------
+/* ---- batch driver: main.m's closed loop (main.m:90-190) for B vehicles ----------------
  * Per simulation step: projection of the plant state onto the track
- * (cartesian_to_curvilinear.m / closest_point.m), x0 and speed-ramp reference (main.m:89-108),
- * the fused LTV-MPC step linearised at the previous prediction (main.m:113-118), then the
- * actuator PIDs and the Cartesian dynamic plant (main.m:146-160, pid_controller.m,
- * integrate_cart_dyn.m).  A vehicle stops when s >= track length (main.m:97).
- *   plant0 [7 x B]; x_opt0 [N_x*N x B], u_opt0 [N_u*N x B]: the initial guess of main.m:42-53.
+ * (cartesian_to_curvilinear.m / closest_point.m), x0 and speed-ramp reference (main.m:92-114),
+ * the fused LTV-MPC step linearised at the previous prediction (main.m:118-127), then the
+ * actuator PIDs and the Cartesian dynamic plant (main.m:166-179, pid_controller.m,
+ * integrate_cart_dyn.m).  A vehicle stops when s >= track length (main.m:102).
+ *   plant0 [7 x B]; x_opt0 [N_x*N x B], u_opt0 [N_u*N x B]: the initial guess of main.m:44-55.
  * Outputs: plant_final [7 x B], steps [B] MPC steps taken; optional histories
- * n_hist [n_sim x B] (lateral deviation, main.m:96), plant_hist [7 x n_sim x B] (x_history),
+ * n_hist [n_sim x B] (lateral deviation, main.m:101), plant_hist [7 x n_sim x B] (x_history),
  * exit_hist [n_sim x B]. */
 int fsae_closed_loop_host(fsae_ctx* ctx, int model, int B, int N_steps, double dt, int n_sim,
                           double target_vel, const int32_t* track_id, const int32_t* param_id,
@@ -246,7 +246,9 @@ int fsae_qpoases_host(fsae_ctx* ctx, int B, int nV, int nC,
 int fsae_debug_counters(fsae_ctx* ctx, uint64_t* out3, int reset);
 /* Select the fused kernel variant: 2 (default) = register-tiled product kernel,
  * 1 = shared-memory variant kept as an in-library cross-check; 21 / 26 / 28 / 29 = other warp
- * counts and block sizes of the register-tiled kernel (tests).  Returns the previous value. */
+ * counts and block sizes of the register-tiled kernel; 31 / 32 = the kinematic solver in integrator
+ * coordinates with the column-lane / row-lane operator layout (tests, horizons 20 and 40; only in the
+ * cross-check build of the library).  Returns the previous value. */
 int fsae_debug_set_kernel_version(fsae_ctx* ctx, int version);
 /* Debug taps of the fused kernel (tests): DEVICE buffers that the following fsae_ltvmpc_dev calls
  * fill, per problem and column-major, with the condensed Hessian H [nV x nV x B]

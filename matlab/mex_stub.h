@@ -8,7 +8,7 @@
 typedef struct mxArray_tag mxArray;
 typedef size_t mwSize;
 typedef enum { mxREAL = 0, mxCOMPLEX = 1 } mxComplexity;
-typedef enum { mxDOUBLE_CLASS = 6, mxINT32_CLASS = 12, mxUINT64_CLASS = 15 } mxClassID;
+typedef enum { mxDOUBLE_CLASS = 6, mxINT8_CLASS = 8, mxINT32_CLASS = 12, mxUINT64_CLASS = 15 } mxClassID;
 double* mxGetPr(const mxArray*);
 void* mxGetData(const mxArray*);
 double mxGetScalar(const mxArray*);

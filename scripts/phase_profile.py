@@ -11,9 +11,22 @@ if not (os.environ.get("FSAE_PROF_NOBUILD") and os.path.exists(prof_so)) and (no
     # the phase counters are __device__ globals: the profile build is ONE translation unit (all TUs included)
     os.makedirs(os.path.dirname(prof_so), exist_ok=True)
     unity = os.path.join(ROOT, "build", "prof_unity.cu")
+    # only the kernel families being profiled are compiled (FSAE_PROF_TUS, default kin40 + dyn40); the others are stubs
+    want = os.environ.get("FSAE_PROF_TUS", "k_kin40,k_dyn40").split(",")
+    allk = {"k_kin40": "launch_kin40", "k_kin20": "launch_kin20", "k_kin80": "launch_kin80", "k_dyn40": "launch_dyn40",
+            "k_dyn20": "launch_dyn20", "k_dyn80": "launch_dyn80"}
     with open(unity, "w") as fh:
-        fh.write("".join(f'#include "{os.path.join(CSRC, f)}"\n' for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")))
-    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DFSAE_PROFILE", "-DFSAE_XCHECK",
+        fh.write(f'#include "{os.path.join(CSRC, "capi.cu")}"\n#include "{os.path.join(CSRC, "k_xcheck.cu")}"\n')
+        for k, fn in allk.items():
+            if k in want:
+                fh.write(f'#include "{os.path.join(CSRC, k + ".cu")}"\n')
+            else:
+                fh.write(f'namespace fsae {{ cudaError_t {fn}(const BatchArgs&, cudaStream_t, int) {{ return cudaErrorNotSupported; }} }}\n')
+        for k in ("kin80", "dyn80"):
+            if "k_" + k not in want:
+                fh.write(f'namespace fsae {{ size_t slab_{k}() {{ return 1; }} }}\n')
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DFSAE_PROFILE"] +
+                   (["-DFSAE_XCHECK"] if os.environ.get("FSAE_PROF_XCHECK") else []) + ["-lineinfo",
                     "-diag-suppress", "128,39", "-shared", "-Xcompiler", "-fPIC", "-o", prof_so, unity], check=True)
 os.environ["FSAE_LIB"] = prof_so
 import fsae_mpc_b200 as fm

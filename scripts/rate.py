@@ -8,6 +8,8 @@ W = {"kin40": ("kinematic", "fsg2019", 65536, 40), "kin20": ("kinematic", "fsg20
      "dyn40": ("dynamic", "fss2019", 32768, 40), "dyn20": ("dynamic", "fss2019", 32768, 20)}
 names = [a for a in sys.argv[1:] if a in W] or ["kin40", "kin20", "dyn40"]
 mpc = fm.FsaeMpc(0)
+if os.environ.get("FSAE_KV"):            # kernel variant of the cross-check library (FSAE_LIB=fsae_mpc_b200/libfsae_mpc_b200_xcheck.so)
+    mpc.set_kernel_version(int(os.environ["FSAE_KV"]))
 tracks = wl.load_tracks()
 for tid, (n, t) in enumerate(tracks.items()):
     mpc.set_track(tid, t[0], t[1], t[2])
@@ -47,7 +49,7 @@ for name in names:
     e1.record(st); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
     a, dr, rf = mpc.counters()
-    print(json.dumps({"workload": name, "lib": os.path.basename(os.environ.get("FSAE_LIB", "product")), "batch": B, "ms_per_step": round(ms, 3),
+    print(json.dumps({"workload": name, "lib": os.path.basename(os.environ.get("FSAE_LIB", "product")) + (":kv" + os.environ["FSAE_KV"] if os.environ.get("FSAE_KV") else ""), "batch": B, "ms_per_step": round(ms, 3),
                       "qps": round(B / ms * 1e3), "exit_nonzero": int((o['exitflag'] != 0).sum().item()),
                       "iters": round(o['iters'].double().mean().item(), 2), "adds": round(a / (B * K), 2), "drops": round(dr / (B * K), 2),
                       "refreshes": round(rf / (B * K), 3), "checksum_u": float(o['u_opt'].double().abs().sum().item())}), flush=True)

@@ -56,9 +56,9 @@ def _certify(mpc, model, track, B, chunk, tid, pid, max_infeasible, N=40):
     import fsae_mpc_b200 as fm
     from fsae_mpc_b200 import workload as wl
     mid = fm.KINEMATIC if model == "kinematic" else fm.DYNAMIC
-    if N == 80:                                                              # the committed fsg2019 lap, perturbed
+    if N == 80:                                                              # the committed horizon-80 laps, perturbed
         from conftest import load_golden, c_layout
-        g = load_golden("kinematic_lap_fsg2019_N80.npz")
+        g = load_golden("kinematic_lap_fsg2019_N80.npz" if model == "kinematic" else "dynamic_lap_fss2019_N80.npz")
         rng = np.random.default_rng(1000)
         pick = rng.integers(g["x0"].shape[0], size=B)
         x0 = g["x0"][pick].copy()
@@ -128,6 +128,18 @@ def test_full_kinematic_batch_is_kkt_certified(mpc):
     """configs[1]: all 65,536 kinematic problems of the bench batch."""
     worst, ninf = _certify(mpc, "kinematic", "fsg2019", 65536, 4096, 0, 0, max_infeasible=0)
     print("kinematic 65,536: worst scaled KKT residuals", worst)
+    assert worst["primal"] <= 1e-7 and worst["active"] <= 1e-7, worst
+    assert worst["stat"] <= 1e-7 and worst["dual"] <= 1e-6, worst
+
+
+def test_dynamic_horizon_80_is_kkt_certified(mpc):
+    """configs[4] names horizons 20 / 40 / 80; the dynamic model (main.m:26, the reference's default) at 80: nV = 164,
+    all packed B_bar rows, the full H and the J staging in the L2 slab.  1,024 perturbed problems of the committed
+    horizon-80 lap on fss2019."""
+    import fsae_mpc_b200 as fm
+    mpc.set_params(3, fm.default_params(fm.DYNAMIC))
+    worst, ninf = _certify(mpc, "dynamic", "fss2019", 1024, 256, 1, 3, max_infeasible=1024 // 20, N=80)
+    print(f"dynamic N=80 fss2019 1,024: infeasible {ninf}, worst scaled KKT residuals", worst)
     assert worst["primal"] <= 1e-7 and worst["active"] <= 1e-7, worst
     assert worst["stat"] <= 1e-7 and worst["dual"] <= 1e-6, worst
 

@@ -13,7 +13,9 @@ CASES = [("kinematic", "kinematic_lap_fsg2019.npz", "fsg2019", 0, 33), ("kinemat
          ("kinematic", "kinematic_lap_fsg2019.npz", "fsg2019", 0, 21), ("kinematic", "kinematic_lap_fsg2019_N80.npz", "fsg2019", 0, 55),
          ("kinematic", "kinematic_lap_fsg2019.npz", "fsg2019", 0, 5),     # the reference's minimum: N_steps = length(x_ref) =
                                                                           # max(size(x_ref)) is only the horizon when N_steps >= N_x
-         ("dynamic", "dynamic_lap_fss2019.npz", "fss2019", 1, 27), ("dynamic", "dynamic_lap_fss2019.npz", "fss2019", 1, 13)]
+         ("dynamic", "dynamic_lap_fss2019.npz", "fss2019", 1, 27), ("dynamic", "dynamic_lap_fss2019.npz", "fss2019", 1, 13),
+         # the dynamic model beyond horizon 40 (all packed B_bar rows in the L2 slab): the capacity itself and a padded one
+         ("dynamic", "dynamic_lap_fss2019_N80.npz", "fss2019", 1, 80), ("dynamic", "dynamic_lap_fss2019_N80.npz", "fss2019", 1, 67)]
 
 
 @pytest.mark.parametrize("model,fixture,track,tid,N", CASES)
@@ -44,7 +46,13 @@ def test_odd_horizons_match_oracle(mpc, model, fixture, track, tid, N):
         assert np.max(np.abs(r.u_opt[j] - u)) <= 1e-6 * max(1.0, np.max(np.abs(u))), j          # north_star tolerance
         assert np.max(np.abs(r.x_opt[j] - x)) <= 1e-6 * max(1.0, np.max(np.abs(x))), j
         assert abs(r.fval[j] - fv) <= 1e-7 * (1 + abs(fv)) and np.max(np.abs(r.slack_opt[j] - sl)) <= 1e-7
-        assert np.array_equal(r.workingSetB[j], info.workingSetB) and np.array_equal(r.workingSetC[j], info.workingSetC), j
+        # same working set; where it differs the constraint must be DEGENERATE in the oracle's solution (active with a
+        # zero multiplier: both working sets describe the same minimiser -- north_star: "the same active set where the
+        # problem is non-degenerate").  Seen at horizon 80 of the dynamic model only.
+        ws_gpu = np.concatenate([r.workingSetB[j], r.workingSetC[j]])
+        ws_ora = np.concatenate([info.workingSetB, info.workingSetC])
+        diff = np.nonzero(ws_gpu != ws_ora)[0]
+        assert len(diff) <= 2 and np.all(np.abs(info.lam[diff]) <= 1e-6 * (1.0 + np.abs(info.lam[:2 * N]).max())), (j, diff, info.lam[diff])
 
 
 def test_horizon_limits_are_reported(mpc):

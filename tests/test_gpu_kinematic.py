@@ -165,11 +165,13 @@ def test_kernel_variants_agree(mpc, mpc_x):
     assert same.mean() > 0.99
 
 
-@pytest.mark.parametrize("kv", [21, 26, 28, 29])
+@pytest.mark.parametrize("kv", [21, 26, 28, 29, 31, 32])
 def test_warp_count_and_block_size_variants_agree(mpc, mpc_x, kv):
     """The dual active-set core is a template over the warp count (tile geometry) and the number of
     constraints taken per search (block size).  Every instantiation must reach the same minimiser and
-    the same working set as the product configuration, whatever its pivot order."""
+    the same working set as the product configuration, whatever its pivot order.
+    31 / 32: the solver in integrator coordinates w = T u (sparse normals), with the column-lane core and with the
+    row-lane core (gi_core_rl.cuh) -- a different operator layout, coordinates and update formulas, same answers."""
     from fsae_mpc_b200 import workload as wl
     x0, xr, xl, ul = wl.perturbed_batch("kinematic", "fsg2019", 1500, seed=11)
     r2 = mpc.ltvmpc_kinetmatic_curvilinear(x0, xr, DT, xl, ul)
