@@ -12,6 +12,7 @@ cudaError_t launch_kin20(const BatchArgs& a, cudaStream_t st, int variant) {
     }
 #endif
     (void)variant;
-    return launch_v2<KinModel, 20, 5, 4, 1>(a, st);                  // 4 warps x 5 CTAs/SM: 4.63M
+    if (a.B <= sm_count()) return launch_v2<KinModel, 20, 2, 8, 1>(a, st);     // latency mode (see k_kin40.cu): 86 vs 112 us
+    return launch_v2<KinModel, 20, 5, 4, 1>(a, st);                  // 4 warps x 5 CTAs/SM
 }
 }  // namespace fsae

@@ -25,6 +25,15 @@ static cudaError_t launch_v2_t(const BatchArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// SMs of the current device (latency-mode dispatch)
+static int sm_count() {
+    static int n[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (!n[dev & 63]) cudaDeviceGetAttribute(&n[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    return n[dev & 63];
+}
+
 // a.N == N: the exact-capacity kernel; a.N < N: the padding kernel (runtime horizon)
 template <class Model, int N, int MINB, int NW = 8, int KB = 1, int CSR = -1>
 static cudaError_t launch_v2(const BatchArgs& a, cudaStream_t st) {
