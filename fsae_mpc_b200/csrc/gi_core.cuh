@@ -127,7 +127,7 @@ struct GiCfg {
     static constexpr int RP = RPW * NW;                      // padded rows
     static constexpr int CS = (NVMAX + 32) / 32;             // column slots per lane (one spare column)
     static constexpr int CP = CS * 32;                       // padded columns
-    static constexpr int SP = (NVMAX > 96) ? 8 : 3;          // partial sums per row of a packed symv (long horizons: H in L2)
+    static constexpr int SP = (NVMAX > 96) ? 8 : 3;          // partial sums per row of a packed symv (long horizons: H in L2); >= 2
     static constexpr bool TWO_LEVEL_SUM = NW_ >= 6;          // cross-warp sum of M'v: slice per warp + second barrier
     static constexpr int CSR = (CSR_ < 0 || CSR_ > CS) ? CS : CSR_;   // column slots held in registers ...
     static constexpr int CSS = CS - CSR;                     // ... and in shared memory (long horizons)
@@ -182,7 +182,7 @@ struct GiSm {
     double zrow[G::RP];                // per-warp reduced z
     double ysum[G::TWO_LEVEL_SUM ? G::CP : 1];   // published cross-warp sums of M'v (two-level variant)
     double xs0[G::RP];                 // x as the block's search saw it (own rows per warp)
-    double wpart[G::SP][G::RP];        // symv partials
+    alignas(16) double wpart[G::SP][G::RP];   // symv partials; between symv's also the (k_i, w_i) pairs of the add update
     double dvec[G::RP];                // LDL' pivots
     double red_val[2][G::NW];
     unsigned long long red_key[2][G::NW * G::KB];   // per-warp top-KB violations (dkey) ...
@@ -269,6 +269,29 @@ struct GiOps {
         const bool writer = (lane & ((1 << SH) - 1)) == 0;
         if (writer && rr < RPW) S.zrow[row0 + rr] = zr;
         __syncwarp();
+    }
+
+    // The same product for the add iteration: the sum of row rr = lane >> SH stays in a REGISTER of the lanes that
+    // the reduce-scatter leaves it in (`holds`: the first lane of each group, rr < RPW) -- x, k and w of that row are
+    // computed by that lane, so z never goes through shared memory.
+    static constexpr int ZSH = (RH == 32) ? 0 : (RH == 16 ? 1 : 2);
+    __device__ __forceinline__ static double matvec_N_reg(const GiTile<G>& m, const double (&y)[CS], int q0, int nV,
+                                                          int& rr, bool& holds) {
+        const int lane = threadIdx.x & 31;
+        double zp[RH];
+#pragma unroll
+        for (int r = 0; r < RH; ++r) zp[r] = 0.0;
+#pragma unroll
+        for (int s = 0; s < CS; ++s) {
+            const int j = lane + 32 * s;
+            const double yj = (j >= q0 && j < nV) ? y[s] : 0.0;
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) zp[r] += m(r, s) * yj;
+        }
+        const double zr = warp_reduce_scatter<RH>(zp);
+        rr = lane >> ZSH;
+        holds = ((lane & ((1 << ZSH) - 1)) == 0) && rr < RPW;
+        return zr;
     }
 
     // rowv = Hp * v (+ addv) for this warp's rows; v full length in shared; one barrier inside
@@ -770,7 +793,21 @@ struct GiOps {
                 }
                 // z = J2 y2 needs only y: issued here so that its FMAs and reduce-scatter shuffles interleave
                 // with the reductions of the step-length phase (independent dependency chains)
-                matvec_N(S, m, y, q, nV);
+                {
+                    // column q (it leaves J2 if p is added): published now, read by the row lanes after the step lengths
+                    const int qs0 = q >> 5, ql0 = q & 31;
+                    if (lane == ql0) {
+#pragma unroll
+                        for (int s = 0; s < CS; ++s)
+                            if (s == qs0) {
+#pragma unroll
+                                for (int r = 0; r < RPW; ++r) S.colk[0][row0 + r] = m(r, s);
+                            }
+                    }
+                }
+                int zrr;
+                bool zholds;
+                const double zr_mine = matvec_N_reg(m, y, q, nV, zrr, zholds);
                 PHASE(5);
                 bool more = true;                   // (piggy-backed only) keep going with this candidate
                 if (KB > 1 && piggy) {
@@ -826,10 +863,7 @@ struct GiOps {
                     PHASE(6);
                     // P5: x += t z  (this warp's rows only)
                     if (primal) {
-                        if (lane < RPW) {
-                            const int i = row0 + lane;
-                            if (i < nV) S.x[i] += t * S.zrow[i];
-                        }
+                        if (zholds && row0 + zrr < nV) S.x[row0 + zrr] += t * zr_mine;
                         sp += t * d2;
                     }
                     if (full && tid == 0) {
@@ -850,14 +884,13 @@ struct GiOps {
                 if (!more || full) {
                     if (more) {
                         // P6a: add p.  K1 <- K1 - k r', J2 <- J2 (I - beta v v'), column q <- k = z/d2
-                        const int qs = q >> 5, ql = q & 31;
-                        if (lane == ql) {
-#pragma unroll
-                            for (int s = 0; s < CS; ++s)
-                                if (s == qs) {
-#pragma unroll
-                                    for (int r = 0; r < RPW; ++r) S.colk[0][row0 + r] = m(r, s);
-                                }
+                        const int qs = q >> 5;
+                        __syncwarp();                       // column q visible to the row lanes
+                        if (zholds) {                       // k_i = z_i / d2,  w_i = beta (z_i + sgd M[i][q]): once per row
+                            double2 kwv;
+                            kwv.x = zr_mine * inv_d2;
+                            kwv.y = (zr_mine + sgd * S.colk[0][row0 + zrr]) * beta;
+                            reinterpret_cast<double2*>(&S.wpart[0][0])[row0 + zrr] = kwv;      // (k_i, w_i): wpart is free between symv's
                         }
                         __syncwarp();
                         // Column slots entirely left of q take  m - kr y,  slots entirely right of it
@@ -879,9 +912,8 @@ struct GiOps {
                             if (qs == qq) {                 // one specialised copy per position of the mixed slot
 #pragma unroll
                                 for (int r = 0; r < RPW; ++r) {
-                                    const double zr = S.zrow[row0 + r];
-                                    const double kr = zr * inv_d2;
-                                    const double wr = (zr + sgd * S.colk[0][row0 + r]) * beta;
+                                    const double2 kwv = reinterpret_cast<const double2*>(&S.wpart[0][0])[row0 + r];
+                                    const double kr = kwv.x, wr = kwv.y;
 #pragma unroll
                                     for (int s = 0; s < CS; ++s) {
                                         if (s < qq) m(r, s) = fma(-kr, y[s], m(r, s));
