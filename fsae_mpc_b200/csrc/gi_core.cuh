@@ -521,30 +521,48 @@ struct GiOps {
             const double ik = 1.0 / kHk;
             const double rs = rsqrt(kHk);
             const int q1 = q - 1, q1s = q1 >> 5, q1l = q1 & 31;
+            // K1 columns j < q, j != l:  m - k (r'_j);  the masked, scaled r' once per lane
+            double rpm[CS];
+#pragma unroll
+            for (int s = 0; s < CS; ++s) {
+                const int j = lane + 32 * s;
+                rpm[s] = (j < q && j != l) ? rp[s] * ik : 0.0;
+            }
 #pragma unroll
             for (int r = 0; r < RPW; ++r) {
                 const double kr = S.colk[1][row0 + r];
 #pragma unroll
-                for (int s = 0; s < CS; ++s) {
-                    const int j = lane + 32 * s;
-                    if (j < q && j != l) m(r, s) -= kr * (rp[s] * ik);
-                }
-                double last = 0.0;
+                for (int s = 0; s < CS; ++s) m(r, s) = fma(-kr, rpm[s], m(r, s));
+            }
+            // column moves through shared memory (this warp's rows only): the updated column q-1 goes into slot l, the
+            // freed direction k / sqrt(k'Hk) becomes column q-1.  Only the two owner lanes touch their registers.
+            const bool mv = (l != q1);
+            if (mv && lane == q1l) {
 #pragma unroll
                 for (int s = 0; s < CS; ++s)
-                    if (s == q1s) last = m(r, s);
-                last = __shfl_sync(0xffffffffu, last, q1l);
+                    if (s == q1s) {
 #pragma unroll
-                for (int s = 0; s < CS; ++s) {
-                    const int j = lane + 32 * s;
-                    if (j == l && l != q1) m(r, s) = last;
-                }
-#pragma unroll
-                for (int s = 0; s < CS; ++s) {
-                    const int j = lane + 32 * s;
-                    if (j == q1) m(r, s) = kr * rs;
-                }
+                        for (int r = 0; r < RPW; ++r) S.colk[0][row0 + r] = m(r, s);
+                    }
             }
+            __syncwarp();
+            if (mv && lane == ll) {
+#pragma unroll
+                for (int s = 0; s < CS; ++s)
+                    if (s == ls) {
+#pragma unroll
+                        for (int r = 0; r < RPW; ++r) m(r, s) = S.colk[0][row0 + r];
+                    }
+            }
+            if (lane == q1l) {
+#pragma unroll
+                for (int s = 0; s < CS; ++s)
+                    if (s == q1s) {
+#pragma unroll
+                        for (int r = 0; r < RPW; ++r) m(r, s) = S.colk[1][row0 + r] * rs;
+                    }
+            }
+            __syncwarp();
             double lam_last = 0.0;
 #pragma unroll
             for (int s = 0; s < CS; ++s)
