@@ -388,9 +388,9 @@ struct MpcProb {
             for (int c = 0; c < C::NXS; ++c) acc[c] = 0.0;
             if (valid) {
                 const int len = NU * (k + 1);
-                const int ch = (((len + 3) >> 2) + 1) & ~1;          // even chunk -> 16-byte aligned pairs
-                const int j0 = part * ch, j1 = (j0 + ch < len) ? j0 + ch : len;
-                for (int j = j0; j < j1; j += 2) {
+                // the four lanes of a step take the column pairs round-robin: consecutive lanes read consecutive
+                // 16-byte pairs of the packed row and of x (a chunk per lane put the lanes a chunk apart: bank conflicts)
+                for (int j = 2 * part; j < len; j += 8) {
                     const double2 xx = *reinterpret_cast<const double2*>(&x[j]);
 #pragma unroll
                     for (int c = 0; c < C::NCR; ++c) {
