@@ -390,16 +390,23 @@ struct MpcProb {
                 const int len = NU * (k + 1);
                 // the four lanes of a step take the column pairs round-robin: consecutive lanes read consecutive
                 // 16-byte pairs of the packed row and of x (a chunk per lane put the lanes a chunk apart: bank conflicts)
+                double accb[C::NCR];                     // second partial sum per row: two 8-cycle chains instead of one of 16
+#pragma unroll
+                for (int c = 0; c < C::NCR; ++c) accb[c] = 0.0;
+#pragma unroll 2
                 for (int j = 2 * part; j < len; j += 8) {
                     const double2 xx = *reinterpret_cast<const double2*>(&x[j]);
 #pragma unroll
                     for (int c = 0; c < C::NCR; ++c) {
                         const double2 bb = *reinterpret_cast<const double2*>(&S.crow(c)[D::pk(k, j)]);
-                        acc[c] = fma(bb.x, xx.x, fma(bb.y, xx.y, acc[c]));
+                        acc[c] = fma(bb.x, xx.x, acc[c]);
+                        accb[c] = fma(bb.y, xx.y, accb[c]);
                     }
 #pragma unroll
                     for (int ci = 0; ci < C::NINT; ++ci) acc[C::NCR + ci] += (C::int_ucol(ci) == 0) ? xx.x : xx.y;
                 }
+#pragma unroll
+                for (int c = 0; c < C::NCR; ++c) acc[c] += accb[c];
             }
 #pragma unroll
             for (int c = 0; c < C::NXS; ++c) {
