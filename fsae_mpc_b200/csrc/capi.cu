@@ -981,11 +981,11 @@ extern "C" int fsae_qpoases_host(fsae_ctx* ctx, int B, int nV, int nC,
                                  const double* lb, const double* ub, const double* lbA, const double* ubA,
                                  double* x, double* fval, int32_t* exitflag, int32_t* iters,
                                  double* lambda, int8_t* workingSetB, int8_t* workingSetC) {
-    constexpr int NVMAX = 95;
+    constexpr int NVMAX = 95, NVBIG = 191;      // two instantiations of the dense kernel (dense_qp.cuh)
     if (!ctx || B < 0 || nV <= 0 || nC < 0 || !H || !g || !lb || !ub || !x || !fval || !exitflag ||
         (nC > 0 && (!A || !lbA || !ubA)))
         return FSAE_ERR_ARG;
-    if (nV > NVMAX) { ctx->err = "fsae_qpoases_host: nV > 95 is not supported by this build"; return FSAE_ERR_UNSUPPORTED; }
+    if (nV > NVBIG) { ctx->err = "fsae_qpoases_host: nV > 191 is not supported by this build"; return FSAE_ERR_UNSUPPORTED; }
     if (B == 0) return FSAE_OK;
     CK(cudaSetDevice(ctx->device));
     const size_t szi[7] = {(size_t)B * nV * nV * 8, (size_t)B * nV * 8, (size_t)B * nC * nV * 8, (size_t)B * nV * 8,
@@ -1011,12 +1011,42 @@ extern "C" int fsae_qpoases_host(fsae_ctx* ctx, int B, int nV, int nC,
     a.wsC = (workingSetC && nC) ? (int8_t*)ctx->out[6].p : nullptr;
     a.feas_tol = ctx->h_params[0].feas_tol; a.flat_eps = ctx->h_params[0].flat_eps; a.max_iter = ctx->h_params[0].max_iter;
     a.counters = ctx->d_counters;
-    const size_t smem = sizeof(DenseSm<NVMAX>) + (size_t)nV + nC + 16;
-    auto kern = dense_qp_kernel<NVMAX>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B, 256, smem, ctx->stream>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
+    a.hscratch = nullptr;
+    if (nV <= NVMAX) {
+        const size_t smem = sizeof(DenseSm<NVMAX>) + (size_t)nV + nC + 16;
+        auto kern = dense_qp_kernel<NVMAX>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<B, 256, smem, ctx->stream>>>(a);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    } else {
+        // 96 <= nV <= 191 (the condensed QPs of horizon 80): 12 warps, half of the operator tile in shared memory, H in the
+        // solver's variable order in a global slab (the pool of the long-horizon fused kernels), launched in slices
+        using DS = DenseSm<NVBIG, 12, 3, true>;
+        const size_t smem = sizeof(DS) + (size_t)nV + nC + 16;
+        if (smem > 232448) { ctx->err = "fsae_qpoases_host: too many rows for the large instantiation (shared memory)"; return FSAE_ERR_UNSUPPORTED; }
+        auto kern = dense_qp_kernel<NVBIG, 12, 3, true>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        constexpr int SLICE = 1024;
+        DevBuf& pool = slab_pool(ctx, ctx->stream);
+        const int nsl = B < SLICE ? B : SLICE;
+        CK(pool.reserve((size_t)nsl * nV * nV * sizeof(double)));
+        for (int lo = 0; lo < B; lo += SLICE) {
+            DenseArgs c = a;
+            c.B = (lo + SLICE <= B) ? SLICE : B - lo;
+            c.hscratch = (double*)pool.p;
+            c.H = a.H + (size_t)lo * nV * nV; c.g = a.g + (size_t)lo * nV; c.A = a.A + (size_t)lo * nC * nV;
+            c.lb = a.lb + (size_t)lo * nV; c.ub = a.ub + (size_t)lo * nV; c.lbA = a.lbA + (size_t)lo * nC; c.ubA = a.ubA + (size_t)lo * nC;
+            c.x = a.x + (size_t)lo * nV; c.fval = a.fval + lo; c.exitflag = a.exitflag + lo;
+            if (a.iters) c.iters = a.iters + lo;
+            if (a.lambda) c.lambda = a.lambda + (size_t)lo * (nV + nC);
+            if (a.wsB) c.wsB = a.wsB + (size_t)lo * nV;
+            if (a.wsC) c.wsC = a.wsC + (size_t)lo * nC;
+            kern<<<c.B, 384, smem, ctx->stream>>>(c);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+    }
     for (int i = 0; i < 7; ++i)
         if (dst[i] && (i != 6 || nC)) CK(cudaMemcpyAsync(dst[i], ctx->out[i].p, szo[i], cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -1,6 +1,9 @@
 // Batched dense QP solve: drop-in for
 //     [x,fval,exitflag,iter,lambda,auxOutput] = qpOASES(H,g,A,lb,ub,lbA,ubA)
-// (optimizers/matlab/qpOASES/qpOASES.m:22) for B independent QPs of one shape, nV <= 95.
+// (optimizers/matlab/qpOASES/qpOASES.m:22) for B independent QPs of one shape.  Two instantiations: nV <= 95
+// (8 warps, operator in registers, packed H in shared memory) and nV <= 191 (12 warps, half of the operator tile in
+// shared memory, H as a full symmetric matrix in a per-problem global slab that stays L2-resident) -- the second
+// covers the condensed QPs of horizon 80 (nV = 161 / 164).
 // Same register-tiled dual active-set core as the fused MPC kernel (gi_core.cuh); here the
 // problem policy reads the dense constraint matrix from global memory (column-major
 // [nC x nV], so consecutive threads read consecutive rows: coalesced).
@@ -23,24 +26,26 @@ struct DenseArgs {
     double feas_tol, flat_eps;
     int max_iter;
     unsigned long long* counters;
+    double* hscratch;       // large instantiation: B x nV x nV doubles (H in the solver's variable order)
 };
 
-template <int NVMAX>
+template <int NVMAX, int NW = 8, int CSR = -1, bool HPG = false>
 struct DenseSm {
-    using G = GiCfg<NVMAX, 8>;
+    using G = GiCfg<NVMAX, NW, 1, CSR>;
     double lbv[NVMAX], ubv[NVMAX];     // variable bounds in internal order
     int perm[NVMAX];                   // internal index -> caller's index
     int nflat, ncurv;
     int pad_[2];
-    GiSm<G, 8> gi;                     // status[] continues into the dynamic tail (nV + nC bytes)
+    alignas(16) double Msm[GiTile<G>::SM_DOUBLES > 0 ? GiTile<G>::SM_DOUBLES : 2];   // shared part of the operator tiles
+    GiSm<G, 8, HPG> gi;                // status[] continues into the dynamic tail (nV + nC bytes)
 };
 
-template <int NVMAX>
+template <int NVMAX, int NW = 8, int CSR = -1, bool HPG = false>
 struct DenseProb {
-    using G = GiCfg<NVMAX, 8>;
+    using G = GiCfg<NVMAX, NW, 1, CSR>;
     static constexpr bool REUSE = false;       // no candidate reuse: a row evaluation is a full global-memory dot product
     __device__ __forceinline__ double eval_code(int) const { return 0.0; }
-    DenseSm<NVMAX>& S;
+    DenseSm<NVMAX, NW, CSR, HPG>& S;
     const double* A;
     const double* lbA;
     const double* ubA;
@@ -80,14 +85,15 @@ struct DenseProb {
     __device__ __forceinline__ bool is_unit(int pslot) const { return pslot < nV; }
 };
 
-template <int NVMAX>
-__global__ void __launch_bounds__(256, 1) dense_qp_kernel(DenseArgs a) {
-    using G = GiCfg<NVMAX, 8>;
-    using SM = GiSm<G, 8>;
+template <int NVMAX, int NW = 8, int CSR = -1, bool HPG = false>
+__global__ void __launch_bounds__(32 * NW, 1) dense_qp_kernel(DenseArgs a) {
+    using G = GiCfg<NVMAX, NW, 1, CSR>;
+    using SM = GiSm<G, 8, HPG>;
     using Ops = GiOps<G, SM>;
+    using DS = DenseSm<NVMAX, NW, CSR, HPG>;
     constexpr int RPW = G::RPW, CS = G::CS, NT = G::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DenseSm<NVMAX>& S = *reinterpret_cast<DenseSm<NVMAX>*>(smem_raw);
+    DS& S = *reinterpret_cast<DS*>(smem_raw);
     SM& Q = S.gi;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row0 = warp * RPW;
     const int b = blockIdx.x, nV = a.nV, nC = a.nC;
@@ -99,6 +105,7 @@ __global__ void __launch_bounds__(256, 1) dense_qp_kernel(DenseArgs a) {
     const double* lbA = a.lbA + (size_t)b * nC;
     const double* ubA = a.ubA + (size_t)b * nC;
 
+    if (HPG && tid == 0) Q.hpg = a.hscratch + (size_t)b * nV * nV;
     for (int i = tid; i < nV + nC; i += NT) Q.status[i] = 0;
     for (int i = tid; i < G::RP; i += NT) { Q.x[i] = 0.0; Q.g[i] = 0.0; Q.rowv[i] = 0.0; Q.nvec[0][i] = 0.0; Q.zrow[i] = 0.0; Q.colk[0][i] = 0.0; Q.colk[1][i] = 0.0; }
     if (tid == 0) {
@@ -133,6 +140,7 @@ __global__ void __launch_bounds__(256, 1) dense_qp_kernel(DenseArgs a) {
     }
     // H tiles (internal order) and the packed copy
     GiTile<G> m;
+    if (G::CSS > 0) m.attach(S.Msm);
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int i = row0 + r;
@@ -142,7 +150,11 @@ __global__ void __launch_bounds__(256, 1) dense_qp_kernel(DenseArgs a) {
             double v = 0.0;
             if (i < nCv && j < nCv) v = H[(size_t)S.perm[j] * nV + S.perm[i]];
             m(r, s) = v;
-            if (i < nV && j <= i) Q.Hp[G::hp(i, j)] = (i < nCv) ? v : (i == j ? a.flat_eps : 0.0);
+            if (HPG) {          // the full symmetric matrix (every (i, j) is some thread's tile entry)
+                if (i < nV && j < nV) a.hscratch[((size_t)b * nV + i) * nV + j] = (i < nCv && j < nCv) ? v : (i == j ? a.flat_eps : 0.0);
+            } else {
+                if (i < nV && j <= i) Q.Hp[G::hp(i, j)] = (i < nCv) ? v : (i == j ? a.flat_eps : 0.0);
+            }
         }
     }
     bad = __syncthreads_or(bad);
@@ -153,7 +165,7 @@ __global__ void __launch_bounds__(256, 1) dense_qp_kernel(DenseArgs a) {
     if (spd && !bad) {
         __syncthreads();
         Ops::initial_point(Q, m, ybuf, q, nCv, nV);
-        const DenseProb<NVMAX> prob{S, A, lbA, ubA, nV, nC};
+        const DenseProb<NVMAX, NW, CSR, HPG> prob{S, A, lbA, ubA, nV, nC};
         st = Ops::solve(prob, Q, m, lam, q, ybuf, nV, a.feas_tol, a.max_iter > 0 ? a.max_iter : 5 * (nV + nC));
     }
     __syncthreads();

@@ -233,7 +233,8 @@ int fsae_closed_loop_host(fsae_ctx* ctx, int model, int B, int N_steps, double d
 /* ---- [x,fval,exitflag,iter,lambda,auxOutput] = qpOASES(H,g,A,lb,ub,lbA,ubA) ----------
  * (optimizers/matlab/qpOASES/qpOASES.m:22) for B independent dense QPs of one shape.
  * H [nV x nV x B] symmetric, A [nC x nV x B] column-major.  lambda [ (nV+nC) x B ] in
- * qpOASES's sign convention.  Optional outputs may be NULL. */
+ * qpOASES's sign convention.  Optional outputs may be NULL.  nV <= 191 (the condensed MPC QPs up to
+ * horizon 80 have nV = 161 / 164); larger problems return FSAE_ERR_UNSUPPORTED. */
 int fsae_qpoases_host(fsae_ctx* ctx, int B, int nV, int nC,
                       const double* H, const double* g, const double* A,
                       const double* lb, const double* ub, const double* lbA, const double* ubA,

@@ -6,7 +6,7 @@ function [x, fval, exitflag, iter, lambda, auxOutput] = qpOASES_b200(H, g, A, lb
 %
 %same arguments, same outputs, same encodings (exitflag 0 / 1 / -1 / -2 / -3, lambda in qpOASES's sign
 %convention, auxOutput.workingSetB / workingSetC with -1 / 0 / +1, qpOASES.m:40-60), solved by the batched
-%dual active-set kernel of the fsae_mpc_b200 library (fsae_qpoases_host, nV <= 95).  This is the literal
+%dual active-set kernel of the fsae_mpc_b200 library (fsae_qpoases_host, nV <= 191: every QP the reference forms up to horizon 80).  This is the literal
 %replacement for the call in mpc/ltv/kinematic/ltvmpc_kinetmatic_curvilinear.m:52 and
 %mpc/ltv/dynamic/ltvmpc_dynamic_curvilinear.m:52; the fused drop-ins ltvmpc_*_curvilinear_b200.m never form H.
 %

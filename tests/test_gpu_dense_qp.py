@@ -69,7 +69,42 @@ def test_dense_qp_bounds_only_and_too_large(mpc):
     o = mpc.qpOASES(H, g, None, -np.ones((B, n)), np.ones((B, n)), None, None)
     assert np.allclose(o["x"], np.clip(-g / 2, -1, 1), atol=1e-12)
     with pytest.raises(fm.FsaeError):
-        mpc.qpOASES(np.tile(np.eye(120), (1, 1, 1)), np.zeros((1, 120)), None, -np.ones((1, 120)), np.ones((1, 120)), None, None)
+        mpc.qpOASES(np.tile(np.eye(200), (1, 1, 1)), np.zeros((1, 200)), None, -np.ones((1, 200)), np.ones((1, 200)), None, None)
+    # 96 <= nV <= 191: the large instantiation (operator tile partly in shared memory, H in a global slab)
+    n = 120
+    H = np.tile(np.eye(n) * 2, (B, 1, 1)); g = rng.normal(size=(B, n)) * 4
+    o = mpc.qpOASES(H, g, None, -np.ones((B, n)), np.ones((B, n)), None, None)
+    assert (o["exitflag"] == 0).all() and np.allclose(o["x"], np.clip(-g / 2, -1, 1), atol=1e-12)
+
+
+@pytest.mark.parametrize("model", ["kinematic", "dynamic"])
+def test_dense_qp_on_horizon_80_condensed_qps(mpc, model):
+    """The literal qpOASES(H,f,xA,lb,ub,lbA,ubA) drop-in on the condensed QPs of horizon 80 (nV = 161 / 164, 480 / 1600
+    rows): the large instantiation of the dense kernel must return the minimiser the fused step returns for the same
+    problems, and a KKT point of the QP it was handed."""
+    import fsae_mpc_b200 as fm
+    from conftest import c_layout, DT
+    from oracle import qp
+    mid = fm.KINEMATIC if model == "kinematic" else fm.DYNAMIC
+    g = load_golden("kinematic_lap_fsg2019_N80.npz" if model == "kinematic" else "dynamic_lap_fss2019_N80.npz")
+    pick = [1, 6, 11]
+    tid = np.full(len(pick), 0 if model == "kinematic" else 1, np.int32)
+    pid = np.full(len(pick), 50 + mid, np.int32)
+    mpc.set_params(50 + mid, fm.default_params(mid))
+    args = (g["x0"][pick], c_layout(g["x_ref"][pick]), DT, c_layout(g["x_lin"][pick]), c_layout(g["u_lin"][pick]))
+    q = mpc.condense(mid, *args, track_id=tid, param_id=pid)
+    step = mpc.ltvmpc_kinetmatic_curvilinear if model == "kinematic" else mpc.ltvmpc_dynamic_curvilinear
+    r = step(*args, track_id=tid, param_id=pid)
+    o = mpc.qpOASES(q["H"], q["f"], q["xA"], q["lb"], q["ub"], q["lbA"], q["ubA"])
+    assert (o["exitflag"] == 0).all() and (r.exitflag == 0).all()
+    nU = r.u_opt.shape[1]
+    scale = np.maximum(1.0, np.abs(r.u_opt).max(axis=1))
+    assert (np.abs(o["x"][:, :nU] - r.u_opt).max(axis=1) / scale).max() < 1e-6
+    assert np.abs(o["x"][:, nU:] - r.slack_opt).max() < 1e-6
+    assert np.max(np.abs(o["fval"] + q["const"] - r.fval) / (1 + np.abs(r.fval))) < 1e-7
+    for b in range(len(pick)):
+        k = qp.kkt_residuals(q["H"][b], q["f"][b], q["xA"][b], q["lb"][b], q["ub"][b], q["lbA"][b], q["ubA"][b], o["x"][b], o["lam"][b])
+        assert max(k["primal"], k["stationarity"], k["complementarity"]) < 1e-7, (b, k)
 
 
 def test_dense_qp_flat_variable_on_its_upper_bound(mpc):
