@@ -1188,7 +1188,7 @@ extern "C" int fsae_debug_set_taps(fsae_ctx* ctx, double* d_H, double* d_g, doub
 // select the fused kernel variant (tests cross-check v1 against v2); returns the previous one
 extern "C" int fsae_debug_set_kernel_version(fsae_ctx* ctx, int v) {
 #ifdef FSAE_XCHECK
-    if (!ctx || (v != 1 && v != 2 && v != 21 && v != 22 && v != 23 && v != 26 && v != 28 && v != 29 && v != 31 && v != 32)) return FSAE_ERR_ARG;
+    if (!ctx || (v != 1 && v != 2 && v != 21 && v != 22 && v != 23 && v != 24 && v != 25 && v != 26 && v != 28 && v != 29 && v != 31 && v != 32)) return FSAE_ERR_ARG;
 #else
     if (!ctx || v != 2) return FSAE_ERR_ARG;     // the product library carries the product kernel only
 #endif

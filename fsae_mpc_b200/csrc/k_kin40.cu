@@ -7,6 +7,8 @@ cudaError_t launch_kin40(const BatchArgs& a, cudaStream_t st, int variant) {
         case 21: return launch_v2_t<KinModel, 40, 1, 8, 1, -1, false>(a, st);     // 8 warps (1 CTA/SM: shared memory)
         case 22: return launch_v2_t<KinModel, 40, 1, 12, 1, -1, false>(a, st);    // 12 warps (latency probe)
         case 23: return launch_v2_t<KinModel, 40, 1, 16, 1, -1, false>(a, st);    // 16 warps (latency probe)
+        case 24: return launch_v2_t<KinModel, 40, 1, 8, 2, -1, false>(a, st);     // 8 warps, blocks of 2 (latency probe)
+        case 25: return launch_v2_t<KinModel, 40, 1, 8, 3, -1, false>(a, st);     // 8 warps, blocks of 3 (latency probe)
         case 26: return launch_v2_t<KinModel, 40, 2, 6, 2, -1, false>(a, st);     // 6 warps, blocks of 2 constraints per search
         case 28: return launch_v2_t<KinModel, 40, 2, 6, 3, -1, false>(a, st);     // 6 warps, blocks of 3
         case 29: return launch_v2_t<KinModel, 40, 2, 4, 1, -1, false>(a, st);     // 4 warps

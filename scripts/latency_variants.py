@@ -19,7 +19,7 @@ for N in (40, 20):
         o = dict(u_opt=torch.empty((256, 2 * N), dtype=torch.float64, device=dev), x_opt=torch.empty((256, 5 * N), dtype=torch.float64, device=dev),
                  exitflag=torch.empty(256, dtype=torch.int32, device=dev), fval=torch.empty(256, dtype=torch.float64, device=dev),
                  slack_opt=torch.empty((256, 1), dtype=torch.float64, device=dev), iters=torch.empty(256, dtype=torch.int32, device=dev))
-        for kv in (2, 21, 22, 23, 29, 31, 32) if N == 40 else (2, 21, 26, 31, 32):
+        for kv in (2, 21, 22, 23, 24, 25, 29, 31, 32) if N == 40 else (2, 21, 26, 31, 32):
             try:
                 mpc.set_kernel_version(kv)
             except Exception as e:
