@@ -931,19 +931,28 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     // follow the recursion stage by stage (adjoint rows of J, below); all meet before the tiles
     // are filled.  With four warps the recursion shares the free-response warp and nothing overlaps.
     static_assert(NW >= 4, "stage map: three chain warps + the free-response warp");
-    // (Running the two recursions on two warps was measured: no gain -- one worker warp fewer, same critical path.)
+    // Small state dimension (kinematic, one matrix entry per lane): ONE recursion warp -- two were measured, no gain (one
+    // worker warp fewer, same critical path).  Larger models (dynamic: 49 entries, two passes per phase) with warps to
+    // spare run the Gramian and the Riccati recursion on TWO warps side by side (they share nothing but A_s and B).
     constexpr bool OVL = NW >= 5;
-    constexpr int GW = OVL ? 3 : NW - 1;                         // recursion warp
-    constexpr int WNT = OVL ? NT - 32 : NT;                      // worker threads
-    const bool worker = !OVL || warp != GW;
-    const int wtid = (OVL && warp > GW) ? tid - 32 : tid;        // worker index
+    constexpr bool TWO_REC = OVL && NW >= 8 && (NX * NX > 32);
+    constexpr int GW = OVL ? 3 : NW - 1;                         // recursion warp (Riccati; both when !TWO_REC)
+    constexpr int GW2 = TWO_REC ? GW + 1 : -1;                   // Gramian warp
+    constexpr int NREC = OVL ? (TWO_REC ? 2 : 1) : 0;
+    constexpr int WNT = NT - 32 * NREC;                          // worker threads
+    const bool worker = !OVL || (warp != GW && warp != GW2);
+    const int wtid = (OVL && warp > GW) ? tid - 32 * NREC : tid; // worker index
     auto wbar = [&]() {
         if (OVL) asm volatile("bar.sync 1, %0;" ::"r"(WNT) : "memory");
         else __syncthreads();
     };
     if (warp == GW) {
         if constexpr (NX * NX <= 32) horizon_recursions_small<Model, N>(S, P, Na);
+        else if constexpr (TWO_REC) horizon_recursions<false, true, Model, N>(S, P, Na);
         else horizon_recursions<true, true, Model, N>(S, P, Na);
+    }
+    if constexpr (TWO_REC) {
+        if (warp == GW2) horizon_recursions<true, false, Model, N>(S, P, Na);
     }
     if (warp == NW - 1) {
         if (lane == 0) {
