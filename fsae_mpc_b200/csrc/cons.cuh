@@ -69,7 +69,7 @@ struct Cons<KinModel> {
     // per-step coefficients from the linearisation point
     // (kinematic_tyre_linearise_constraints.m:18-26): C = [0 0 0 2 v d, v^2]/(lf+lr), g0 = v^2 d/(lr+lf)
     __device__ static void step_coefs(const double* xl, const double* ul, const DevTrack& tr,
-                                      const fsae_params& p, double* pc, double* g0) {
+                                      const fsae_params& p, double* pc, double* g0, const KinModel::Aux* = nullptr) {
         const double L = p.lr + p.lf;
         pc[0] = 2.0 * xl[3] * xl[4] / L;
         pc[1] = xl[3] * xl[3] / L;
@@ -205,10 +205,13 @@ struct Cons<DynModel> {
         }
     }
 
+    // aux: the tyre-force terms of the model evaluation AT (xl, ul), if the caller has them (linearise_step hands out
+    // those of its first stage: one model evaluation per step saved); else they are evaluated here
     __device__ static void step_coefs(const double* xl, const double* ul, const DevTrack& tr,
-                                      const fsae_params& p, double* pc, double* g0) {
+                                      const fsae_params& p, double* pc, double* g0, const DynAux* aux = nullptr) {
         DynAux a;
-        DynModel::eval_aux(xl, ul, tr, p, nullptr, nullptr, &a);
+        if (aux) a = *aux;
+        else DynModel::eval_aux(xl, ul, tr, p, nullptr, nullptr, &a);
         const double ih = 1.0 / a.x_d_hat;
         pc[0] = a.denom_vr2 * a.vr * a.x_d_hat_d * ih;
         pc[1] = -a.denom_vr2 * ih;

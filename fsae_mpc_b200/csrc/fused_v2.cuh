@@ -896,7 +896,8 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
     if (tid < N) {
         const int k = tid;
         double Ac[NX * NX], Bc_[NX * NU], dc[NX];
-        linearise_step<Model>(P.lin_scheme, S.xl + k * NX, S.ul + k * NU, dt, tr, P, Ac, Bc_, dc);
+        typename Model::Aux aux;
+        linearise_step<Model>(P.lin_scheme, S.xl + k * NX, S.ul + k * NU, dt, tr, P, Ac, Bc_, dc, &aux);
 #pragma unroll
         for (int i = 0; i < C::NREAL; ++i) {
             const int r = C::real_state(i);
@@ -910,7 +911,7 @@ __global__ void __launch_bounds__(32 * NW_, MINB) ltvmpc_fused_v2_kernel(BatchAr
 #pragma unroll
             for (int i = 0; i < NX * NU; ++i) S.B1[i] = Bc_[i] * dt;   // QUIRK: B(:,:,1) everywhere
         }
-        C::step_coefs(S.xl + k * NX, S.ul + k * NU, tr, P, S.pc + k * C::NPC, S.g0 + k * C::NG0);
+        C::step_coefs(S.xl + k * NX, S.ul + k * NU, tr, P, S.pc + k * C::NPC, S.g0 + k * C::NG0, &aux);
     } else if (tid == N) {
         C::problem_consts(P, S.cg);
     }

@@ -44,6 +44,7 @@ __device__ __forceinline__ double curvature(const DevTrack& tr, double s) {
 
 // ------------------------------------------------------------------ kinematic bicycle
 struct KinModel {
+    struct Aux {};                          // (nothing of the model evaluation is reused by the constraint linearisation)
     static constexpr int NX = 5;
     static constexpr int NU = 2;
     static constexpr int NS = 1;            // slack variables
@@ -92,6 +93,10 @@ struct KinModel {
         A[2 * 5 + 4] = v * c_b * beta_d / lr - s_delta * k;
     }
     // column of the constant continuous-time B that control j drives
+    __device__ __forceinline__ static void eval_first(const double* x, const double* u, const DevTrack& tr,
+                                                      const fsae_params& p, double* f, double* A, Aux*) {
+        eval(x, u, tr, p, f, A);
+    }
     __device__ __forceinline__ static int bcol_state(int j) { return j == 0 ? 3 : 4; }
 };
 
@@ -101,6 +106,7 @@ struct DynAux {     // extra outputs of A_curv_dyn.m:1 used by the constraint li
 };
 
 struct DynModel {
+    using Aux = DynAux;                     // tyre-force terms at the linearisation point, reused by Cons<DynModel>::step_coefs
     static constexpr int NX = 7;
     static constexpr int NU = 2;
     static constexpr int NS = 4;
@@ -197,6 +203,11 @@ struct DynModel {
                                 const fsae_params& p, double* f, double* A) {
         eval_aux(x, u, tr, p, f, A, nullptr);
     }
+    // the evaluation AT the linearisation point (first stage of every RK scheme), handing out the shared terms
+    __device__ static void eval_first(const double* x, const double* u, const DevTrack& tr,
+                                      const fsae_params& p, double* f, double* A, Aux* aux) {
+        eval_aux(x, u, tr, p, f, A, aux);
+    }
     __device__ __forceinline__ static int bcol_state(int j) { return j == 0 ? 3 : 6; }
 };
 
@@ -206,7 +217,7 @@ struct DynModel {
 template <class Model>
 __device__ void linearise_step(int scheme, const double* x, const double* u, double dt,
                                const DevTrack& tr, const fsae_params& p,
-                               double* A, double* Bm, double* d) {
+                               double* A, double* Bm, double* d, typename Model::Aux* aux0 = nullptr) {
     constexpr int NX = Model::NX, NU = Model::NU;
     double f[NX];
     auto matmul_IpA = [&](const double* F, const double* K, double h, double* out) {
@@ -234,14 +245,14 @@ __device__ void linearise_step(int scheme, const double* x, const double* u, dou
             }
     };
     if (scheme == FSAE_LIN_EULER) {
-        Model::eval(x, u, tr, p, f, A);
+        Model::eval_first(x, u, tr, p, f, A, aux0);
 #pragma unroll
         for (int r = 0; r < NX; ++r)
 #pragma unroll
             for (int c = 0; c < NU; ++c) Bm[r * NU + c] = (r == Model::bcol_state(c)) ? 1.0 : 0.0;
     } else if (scheme == FSAE_LIN_RK2) {
         double k1[NX], A1[NX * NX], A2[NX * NX], xt[NX], B1[NX * NU];
-        Model::eval(x, u, tr, p, k1, A1);
+        Model::eval_first(x, u, tr, p, k1, A1, aux0);
 #pragma unroll
         for (int i = 0; i < NX; ++i) xt[i] = x[i] + k1[i] * dt / 2;
         Model::eval(xt, u, tr, p, f, A2);
@@ -255,7 +266,7 @@ __device__ void linearise_step(int scheme, const double* x, const double* u, dou
         double k1[NX], k2[NX], k3[NX], k4[NX], xt[NX];
         double F1[NX * NX], F2[NX * NX], F3[NX * NX], F4[NX * NX], K2[NX * NX], K3[NX * NX], K4[NX * NX];
         double U1[NX * NU], U2[NX * NU], U3[NX * NU], U4[NX * NU];
-        Model::eval(x, u, tr, p, k1, F1);
+        Model::eval_first(x, u, tr, p, k1, F1, aux0);
 #pragma unroll
         for (int i = 0; i < NX; ++i) xt[i] = x[i] + k1[i] * dt / 2;
         Model::eval(xt, u, tr, p, k2, F2);
