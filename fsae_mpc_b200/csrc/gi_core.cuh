@@ -9,11 +9,14 @@
 // lives in REGISTERS (GiTile; long horizons keep some column slots in shared memory): warp w owns rows
 // w*RPW .. w*RPW+RPW-1, lane l owns columns l, l+32, ... (an RPW x CS tile per thread).  One iteration:
 //   exact arg-min of the violations with two 32-bit REDUX per warp on an order-preserving key,
-//   y = M'n (one cross-warp sum through smem; a variable bound publishes a row of M instead),
-//   z = J2 y2 (in-warp reduce-scatter), step lengths and the add/drop decision computed redundantly
-//   by every warp, then either
+//   y = M'n (one cross-warp sum through smem; a normal with at most three entries -- SpN: variable bounds, rows on
+//   integrator coordinates -- is a combination of rows of M that their owner warps publish instead: no dense
+//   normal, no product),
+//   z = J2 y2 (in-warp reduce-scatter; z_i stays in a register of the lane it ends up in, which alone updates x_i
+//   and computes the row scalars k_i, w_i of the add), step lengths and the add/drop decision computed
+//   redundantly by every warp, then either
 //   add : Householder on J2 + rank-1 on K1 (one FMA per element outside the column slot of q), or
-//   drop: K1 += k r'^T with r' = -K1' H k / k'Hk, column swap by shuffle.
+//   drop: K1 += k r'^T with r' = -K1' H k / k'Hk, the two column moves through shared memory by their owner lanes.
 // Termination: a refresh (Newton step on the active manifold, multipliers from stationarity) after
 // every run of partial steps; columns whose recomputed multiplier is negative are dropped.
 // Template knobs (GiCfg): warps per problem NW, constraints taken per search KB (block adds),
